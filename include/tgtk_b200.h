@@ -1,0 +1,166 @@
+/*
+ * tgtk_b200.h -- C ABI of the B200-native time-stepping library (libtgtk_b200.so).
+ *
+ * The reference (m1balcerak/TumorGrowthToolkit) is pure Python and has NO FFI / plugin
+ * layer: its boundary for this path is the Python class API.  This header
+ * is the C ABI introduced BENEATH that API; every entry point names the reference code it
+ * replaces.  The Python mirror (tumorgrowthtoolkit_b200/) binds it with ctypes; the stub a
+ * reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only: pointers, sizes, doubles; no torch / CUDA types in signatures
+ *     (streams and device pointers travel as void* / unsigned long long).
+ *   - every call returns 0 on success, non-zero on failure; tgtk_last_error() returns the
+ *     message of the calling thread's last failure.  No exceptions cross the boundary.
+ *   - host arrays are float64 (the reference's dtype) described by ELEMENT strides, so the
+ *     reference's non-contiguous crop views (FK/FK.py:69-71) can be passed as they are.
+ *     The library owns all device memory of a simulation; the caller owns host memory.
+ *   - a simulation is bound to one device and one stream; calls on one simulation must
+ *     come from one thread at a time.  No global mutable state besides the error string.
+ *   - boundary conditions are periodic in all three axes (np.roll, FK/FK.py:36-38).
+ */
+#ifndef TGTK_B200_H
+#define TGTK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TGTK_ABI_VERSION 1
+
+/* which reference operator a simulation steps */
+enum tgtk_model {
+    TGTK_MODEL_FK = 0,     /* FK.Solver: get_D + FK_update            FK/FK.py:10-42,212-223        */
+    TGTK_MODEL_FK_2C = 1,  /* FK_2c.Solver: get_D_with_necro + FK_2c_update  FK_2c/FK_2c.py:10-76,228-243 */
+    TGTK_MODEL_DTI = 2,    /* FK_DTI_Solver: get_D_from_DTI + FK_update  FK_DTI/FK_DTI.py:25-47,195-211 */
+    TGTK_MODEL_COEF6 = 3,  /* FK_update with six caller-given coefficient arrays   FK/FK.py:34-42 */
+    TGTK_MODEL_FK_FACES = 4, /* FK with the three face arrays built in the reference's exact
+                               rounding order (bit-exact fp64 mode)    FK/FK.py:10-32 */
+    TGTK_MODEL_FK2C_COEF12 = 5 /* FK_2c_update with twelve caller-given coefficient arrays
+                                  FK_2c/FK_2c.py:48-73 */
+};
+
+enum tgtk_dtype { TGTK_F64 = 0, TGTK_F32 = 1 };
+
+/* arrays a caller can upload / download (tgtk_sim_upload / tgtk_sim_download) */
+enum tgtk_field {
+    TGTK_FIELD_U = 0, /* FK / DTI / COEF6 tumour density; FK_2c: P */
+    TGTK_FIELD_P = 0,
+    TGTK_FIELD_N = 1,
+    TGTK_FIELD_S = 2,
+    TGTK_FIELD_WM = 10,
+    TGTK_FIELD_GM = 11,
+    TGTK_FIELD_PC = 12, /* tgtk_faces_host only: P and N of the necrotic closure */
+    TGTK_FIELD_NC = 13,
+    TGTK_FIELD_COEF0 = 20 /* DTI: 20..22 = D_x,D_y,D_z (= rgb[...,a]*Dw);
+                             COEF6: 20..25 = D_plus_x,y,z, D_minus_x,y,z;
+                             FK2C_COEF12: 20..25 as COEF6 for P, 26..31 the same for S */
+};
+
+enum tgtk_stop {
+    TGTK_STOP_NONE = 0,
+    TGTK_STOP_VOLUME = 1, /* volume >= stopping_volume                  FK/FK.py:216-218 */
+    TGTK_STOP_SMALL = 2   /* FK_DTI only: volume < small_volume (1e-6)  FK_DTI/FK_DTI.py:203-206 */
+};
+
+typedef struct tgtk_params {
+    int32_t model;           /* enum tgtk_model */
+    int32_t dtype;           /* enum tgtk_dtype: storage + arithmetic type of the state */
+    int32_t X, Y, Z;         /* cropped box, C order, axis 2 fastest */
+    int32_t logical_or_faces; /* 1: tissue maps are booleans and '+' is logical OR (numpy bool
+                                 quirk); FK_FACES model only */
+    double h[3];             /* dx, dy, dz (already divided by resolution_factor) */
+    double dt;               /* stopping_time / Nt                      FK/FK.py:186 */
+    double rho;              /* proliferation rate 'f'                  FK/FK.py:122 */
+    double Dw;               /* FK, FK_2c (DTI: folded into COEF arrays by the caller) */
+    double ratio;            /* RatioDw_Dg                              FK/FK.py:130 */
+    double th_matter;        /* FK/FK.py:131 */
+    double th_necro;         /* FK_2c/FK_2c.py:154 */
+    double Ds;               /* D_s        FK_2c/FK_2c.py:143 */
+    double lambda_np;        /* FK_2c/FK_2c.py:141 */
+    double sigma_np;         /* FK_2c/FK_2c.py:142 */
+    double lambda_s;         /* FK_2c/FK_2c.py:144 */
+    double stopping_volume;  /* +inf: never                             FK/FK.py:119 */
+    double small_volume;     /* 0: off; FK_DTI passes 1e-6              FK_DTI/FK_DTI.py:203 */
+} tgtk_params;
+
+typedef struct tgtk_status {
+    int32_t steps_run;   /* number of update steps executed (= index of the stop step + 1) */
+    int32_t stop_reason; /* enum tgtk_stop */
+    int32_t stop_step;   /* t of the step that tripped the stop test, -1 if none */
+    int32_t snapshots;   /* number of valid snapshots recorded so far */
+    double last_volume;  /* FK/DTI: dx*dy*dz*sum(u); FK_2c: dx*dy*dz*sum(P)+sum(N) (sic, FK_2c.py:235) */
+    double loop_ms;      /* device time of the launches issued by the last tgtk_sim_run (CUDA events) */
+    int64_t kernel_launches; /* step-kernel launches issued so far */
+} tgtk_status;
+
+typedef struct tgtk_sim tgtk_sim;
+
+int tgtk_abi_version(void);
+const char *tgtk_last_error(void);
+int tgtk_device_count(int *count);
+
+/* Create a simulation on `device`.  `stream` is a cudaStream_t passed as void* (NULL: the
+ * library creates its own non-blocking stream).  Replaces the array set-up part of
+ * Solver.solve() after cropping (FK/FK.py:197-208). */
+int tgtk_sim_create(tgtk_sim **out, const tgtk_params *params, int device, void *stream);
+void tgtk_sim_destroy(tgtk_sim *sim);
+
+/* Host -> device.  `host` is float64 with element strides (sx,sy,sz); any strides are
+ * accepted (rows with sz==1 are copied directly, otherwise gathered on the host).  If
+ * `pinned` is non-zero the caller promises page-locked memory and the copy is fully
+ * asynchronous on the simulation's stream. */
+int tgtk_sim_upload(tgtk_sim *sim, int field, const double *host, const int64_t strides[3], int pinned);
+/* Device -> host (float64, element strides). Synchronises the stream. */
+int tgtk_sim_download(tgtk_sim *sim, int field, double *host, const int64_t strides[3]);
+
+/* Finish set-up once all inputs are uploaded: builds the per-voxel coefficient arrays
+ * (get_D, FK/FK.py:22-32; get_D(…,D_s,1), FK_2c/FK_2c.py:216), resets the step counter. */
+int tgtk_sim_prepare(tgtk_sim *sim);
+
+/* Enqueue `nsteps` update steps (the body of the reference's `for t in range(...)` loops:
+ * update, volume, stop test, snapshot).  `record_steps` (sorted, may be NULL) are absolute
+ * step indices after which the state is snapshotted (FK/FK.py:221-223).  Asynchronous. */
+int tgtk_sim_run(tgtk_sim *sim, int nsteps, const int32_t *record_steps, int nrecord);
+
+/* Wait for the stream and report where the loop stands. */
+int tgtk_sim_sync(tgtk_sim *sim, tgtk_status *status);
+
+/* Per-step volumes of steps [first, first+count) as the device computed them. */
+int tgtk_sim_volumes(tgtk_sim *sim, int first, int count, double *out);
+
+/* Copy snapshot `index` (0-based, in record order) of `field` to the host. */
+int tgtk_sim_snapshot(tgtk_sim *sim, int index, int field, double *host, const int64_t strides[3]);
+
+/* Device pointer of the CURRENT state buffer of `field` (for zero-copy interop, e.g. halo
+ * exchange with torch.distributed), its element pitches and dtype size. */
+int tgtk_sim_device_ptr(tgtk_sim *sim, int field, unsigned long long *ptr, int64_t pitches[3], int *elem_size);
+
+/* One-call convenience used by the Python mirror's public per-step methods
+ * (FK_update(A, D_domain, ...), FK/FK.py:34-42): upload, one step, download. */
+int tgtk_fk_update_host(const tgtk_params *params, int device, double *A, const int64_t a_strides[3],
+                        const double *const coef[6], const int64_t coef_strides[6][3]);
+
+/* FK_2c_update(P,N,S,D_domain,...,D_s_domain,...) on host arrays, in place
+ * (FK_2c/FK_2c.py:48-73): D = D_plus_x,y,z,D_minus_x,y,z for P, Ds the same for S. */
+int tgtk_fk2c_update_host(const tgtk_params *params, int device, double *P, const int64_t p_strides[3],
+                          double *N, const int64_t n_strides[3], double *S, const int64_t s_strides[3],
+                          const double *const D[6], const int64_t d_strides[6][3],
+                          const double *const Ds[6], const int64_t ds_strides[6][3]);
+
+/* m_Tildas / get_D / m_Tildas_with_necro / get_D_with_necro on the device, in the
+ * reference's rounding order (FK/FK.py:10-32, FK_2c/FK_2c.py:10-46).  `what`: 0 = D_minus
+ * faces Dw*(WM_t + GM_t/ratio), 1 = WM_tilda, 2 = GM_tilda.  P and N may both be NULL (no
+ * necrotic closure).  Outputs are dense float64 (X,Y,Z); D_plus_a is np.roll(D_minus_a,1,a). */
+int tgtk_faces_host(int device, int X, int Y, int Z, const double *wm, const int64_t wm_strides[3],
+                    const double *gm, const int64_t gm_strides[3], const double *P, const int64_t p_strides[3],
+                    const double *N, const int64_t n_strides[3], double th, double th_necro, double Dw,
+                    double ratio, int logical_or, int what, double *out_x, double *out_y, double *out_z);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TGTK_B200_H */

@@ -1,0 +1,132 @@
+"""Single-species Fisher-Kolmogorov solver on the B200.
+
+Same constructor / solve() / result-dict contract as the reference's
+TumorGrowthToolkit/FK/FK.py (class Solver, :6-250); the time loop (:212-226) and the per-step
+methods run in libtgtk_b200's CUDA kernels.  Extra optional parameters (all default to the
+reference's behaviour):
+
+    precision   'fp64' (default) | 'fp32'   storage + arithmetic type of the loop
+    device      CUDA device ordinal (default 0)
+    bit_exact   True: fp64 results equal numpy's bit for bit (slower face-array kernel)
+"""
+import numpy as np
+
+from .. import _host, _loop, _ops
+from ..base_solver import BaseSolver
+
+
+class Solver(BaseSolver):
+    def __init__(self, params):
+        super().__init__(params)
+
+    # ---- per-step operators (public in the reference; kept callable) ------------------------
+    def m_Tildas(self, WM, GM, th):
+        """Face-averaged tissue maps, FK.py:10-20 (device kernel, reference rounding)."""
+        return _ops.tissue_tildas(WM, GM, th, device=self._device())
+
+    def get_D(self, WM, GM, th, Dw, Dw_ratio):
+        """Six face-coefficient arrays, FK.py:22-32."""
+        return _ops.face_coefficients(WM, GM, th, Dw, Dw_ratio, device=self._device())
+
+    def FK_update(self, A, D_domain, f, dt, dx, dy, dz):
+        """One explicit Euler step, in place, FK.py:34-42.  Returns the same array object."""
+        return _ops.fk_update(A, D_domain, f, dt, dx, dy, dz, device=self._device())
+
+    # ---- set-up helpers ---------------------------------------------------------------------
+    def crop_tissues_and_tumor(self, GM, WM, tumor_initial, margin=2, threshold=0.05):
+        """Crop to the bounding box of GM+WM >= threshold plus margin (FK.py:44-73)."""
+        box = _host.bounding_box(GM + WM >= threshold, margin, GM.shape)
+        return _host.crop(GM, box), _host.crop(WM, box), _host.crop(tumor_initial, box), box
+
+    def restore_tumor(self, original_shape, tumor, crop_coords):
+        """Paste a cropped field back into a zero volume (FK.py:75-90)."""
+        return _host.paste(original_shape, tumor, crop_coords)
+
+    def gauss_sol3d(self, x, y, z, dx, dy, dz, init_scale):
+        """Clipped Gaussian seed on caller-given coordinate arrays (FK.py:92-105)."""
+        r2 = np.power(x * dx / init_scale, 2) + np.power(y * dy / init_scale, 2) + np.power(z * dz / init_scale, 2)
+        g = 250 / np.power(4 * np.pi * 5.0, 3 / 2) * np.exp(-r2 / (4 * 5.0))
+        g = np.where(g > 0.1, g, 0)
+        return np.where(g > 1, np.float64(1), g)
+
+    def get_initial_configuration(self, Nx, Ny, Nz, NxT, NyT, NzT, r):
+        """Box-shaped seed (FK.py:107-114; unused by solve(), kept for API parity)."""
+        A = np.zeros([Nx, Ny, Nz])
+        if r == 0:
+            A[NxT, NyT, NzT] = 1
+        else:
+            A[NxT - r:NxT + r, NyT - r:NyT + r, NzT - r:NzT + r] = 1
+        return A
+
+    def _device(self):
+        return int(self.params.get('device', 0)) if isinstance(self.params, dict) else 0
+
+    # ---- solve ------------------------------------------------------------------------------
+    def solve(self):
+        p = self.params
+        stopping_time = p.get('stopping_time', 100)
+        stopping_volume = p.get('stopping_volume', np.inf)
+        Dw, rho = p['Dw'], p['rho']
+        gm, wm = p['gm'], p['wm']
+        pct = (p['NxT1_pct'], p['NyT1_pct'], p['NzT1_pct'])
+        res_factor = p['resolution_factor']
+        ratio = p.get('RatioDw_Dg', 10.)
+        th_matter = p.get('th_matter', 0.1)
+        spacing = (p.get('dx_mm', 1.), p.get('dy_mm', 1.), p.get('dz_mm', 1.))
+        init_scale = p.get('init_scale', 1.)
+        n_series = p.get('time_series_solution_Nt', None)
+        verbose = p.get('verbose', False)
+
+        _host.check_tissue_inputs(gm, wm, pct)
+
+        gm_lo = _host.resample_linear(gm, res_factor)
+        wm_lo = _host.resample_linear(wm, res_factor)
+        grid = _host.LowResGrid(gm_lo.shape, gm.shape, res_factor, *spacing, pct)
+        dx, dy, dz = grid.h
+
+        result = {}
+        if gm_lo[grid.seed] == 0 and wm_lo[grid.seed] == 0:          # FK.py:177-182
+            result['error'] = 'Initial tumor position is outside the brain matter'
+            result['success'] = False
+            if verbose:
+                print('Initial tumor position is outside the brain matter')
+            return result
+
+        # FK.py:185: Nt = max(T*Dw/min(h)^2*8 + 100, T*rho*1.1)
+        nt = np.max([stopping_time * Dw / np.power(np.min([dx, dy, dz]), 2) * 8 + 100, stopping_time * rho * 1.1])
+        nsteps, dt = _host.steps_and_dt(nt, stopping_time)
+        if verbose:
+            print(f'Number of simulation timesteps: {nsteps}')
+
+        initial = _host.seed_gaussian(grid, init_scale)
+        box = _host.bounding_box(gm_lo + wm_lo >= 0.5, 2, gm_lo.shape)   # FK.py:197
+        record = _host.record_schedule(nsteps, n_series)
+
+        try:
+            run = _loop.fk_loop(_host.crop(initial, box), _host.crop(wm_lo, box), _host.crop(gm_lo, box),
+                                th_matter, Dw, ratio, rho, dt, dx, dy, dz, nsteps,
+                                stopping_volume=stopping_volume, record_steps=record,
+                                precision=p.get('precision', 'fp64'), device=self._device(),
+                                bit_exact=bool(p.get('bit_exact', False)))
+            volume = np.float64(run['volume'])
+            final_time = run['t_stop'] * dt if run['stop'] == 'volume' else stopping_time
+            final = _host.paste(grid.shape, run['state'], box)
+
+            result['initial_state'] = grid.upsample(initial)
+            result['final_state'] = grid.upsample(final)
+            result['final_time'] = final_time
+            result['final_volume'] = volume
+            result['stopping_criteria'] = 'volume' if volume >= stopping_volume else 'time'
+            result['time_series'] = (np.array([grid.upsample(_host.paste(grid.shape, s, box))
+                                               for s in run['snapshots']]) if record is not None else None)
+            result['Dw'] = Dw
+            result['rho'] = rho
+            result['success'] = True
+            result['NxT1_pct'], result['NyT1_pct'], result['NzT1_pct'] = pct
+            # not part of the reference's result dict: kept on the instance for benchmarks
+            self.last_loop_stats = {'steps_run': run['steps_run'], 'loop_ms': run.get('loop_ms'),
+                                    'voxels': int(np.prod(run['state'].shape))}
+        except Exception as e:                                        # FK.py:246-248
+            result['error'] = str(e)
+            result['success'] = False
+        return result

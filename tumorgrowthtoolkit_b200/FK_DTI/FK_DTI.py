@@ -1,0 +1,110 @@
+"""DTI-driven Fisher-Kolmogorov solver on the B200.
+
+Same contract as the reference's TumorGrowthToolkit/FK_DTI/FK_DTI.py (class FK_DTI_Solver,
+:21-237).  As in the reference, only the tensor DIAGONAL drives the diffusion and D_plus
+aliases D_minus (:39-45), i.e. the operator is sum_a D_aa(c)*(u[c-1]-2u[c]+u[c+1])/h_a^2.
+Optional extra parameters: precision ('fp64' | 'fp32'), device.
+"""
+import numpy as np
+
+from .. import _host, _loop
+from ..FK.FK import Solver as FK_Solver
+from . import tools
+
+
+class FK_DTI_Solver(FK_Solver):
+    def __init__(self, params):
+        super().__init__(params)
+
+    def get_D_from_DTI(self, dtiRGB, DwMax, maskOut=None):
+        """Per-axis coefficients from the normalised tensor diagonal (FK_DTI.py:25-47).
+        Like the reference, D_plus_a IS D_minus_a (same object) and maskOut zeroes dtiRGB in place."""
+        if maskOut is not None:
+            dtiRGB[maskOut] = 0
+        out = {}
+        for a, name in enumerate("xyz"):
+            out["D_minus_" + name] = dtiRGB[:, :, :, a] * DwMax
+        for name in "xyz":
+            out["D_plus_" + name] = out["D_minus_" + name]
+        return out
+
+    def crop_tissues_and_tumor(self, tissue, tumor_initial, brainmask, margin=2, threshold=0.0):
+        """Crop to the bounding box of brainmask > threshold plus margin (FK_DTI.py:49-74)."""
+        box = _host.bounding_box(brainmask > threshold, margin, brainmask.shape)
+        return _host.crop(tissue, box), _host.crop(tumor_initial, box), box
+
+    def solve(self, doPlot=False):
+        p = self.params
+        stopping_time = p.get('stopping_time', 100)
+        stopping_volume = p.get('stopping_volume', np.inf)
+        Dw, rho = p['Dw'], p['rho']
+        scaling = p['diffusionEllipsoidScaling']
+        print(f'diffusionEllipsoidScaling: {scaling}')                 # FK_DTI.py:86 (unconditional)
+        exponent = p.get('diffusionTensorExponent', 1)
+        linear = p.get('diffusionTensorLinear', 0)
+        pct = (p['NxT1_pct'], p['NyT1_pct'], p['NzT1_pct'])
+        res_factor = p['resolution_factor']
+        spacing = (p.get('dx_mm', 1.), p.get('dy_mm', 1.), p.get('dz_mm', 1.))
+        init_scale = p.get('init_scale', 1.)
+        n_series = p.get('time_series_solution_Nt', None)
+        verbose = p.get('verbose', False)
+
+        tensors = p["diffusionTensors"]
+        if scaling != 1:                                                # FK_DTI.py:107-110
+            tensors = tools.elongate_tensor_along_main_axis_torch(tensors, scaling)
+        rgb = tools.makeXYZ_rgb_from_tensor(tensors, exponent=exponent, linear=linear)
+
+        assert isinstance(rgb, np.ndarray), "sRGB must be a numpy array"
+        assert rgb.ndim == 4, "sRGB must be a 4D numpy array, with the last dimension being 3 (RGB)"
+        _host.check_seed(pct)
+
+        rgb_lo = _host.resample_linear(rgb, [res_factor, res_factor, res_factor, 1])
+        if doPlot:                                                      # plotting is out of scope
+            raise NotImplementedError("doPlot=True needs matplotlib and is not part of the time-stepping path")
+        grid = _host.LowResGrid(rgb_lo.shape, rgb.shape, res_factor, *spacing, pct)
+        dx, dy, dz = grid.h
+
+        # FK_DTI.py:156: the max runs over the FULL-resolution rgb
+        nt = np.max([stopping_time * Dw * np.max(rgb) / np.power(np.min([dx, dy, dz]), 2) * 8 + 100,
+                     stopping_time * rho * 1.1])
+        nsteps, dt = _host.steps_and_dt(nt, stopping_time)
+        if verbose:
+            print(f'Number of simulation timesteps: {nsteps}')
+
+        initial = _host.seed_gaussian(grid, init_scale)
+        print("init: ", initial.shape, "Volume of init Tumor", np.sum(initial))   # FK_DTI.py:164
+        brainmask = np.max(rgb_lo, axis=-1) > 0
+        box = _host.bounding_box(brainmask > 0.5, 2, brainmask.shape)             # FK_DTI.py:171
+        record = _host.record_schedule(nsteps, n_series)
+
+        result = {}
+        try:
+            result['success'] = False
+            if not brainmask[grid.seed]:
+                raise ValueError("Origin not within brainmask")
+            run = _loop.dti_loop(_host.crop(initial, box), _host.crop(rgb_lo, box), Dw, rho, dt, dx, dy, dz, nsteps,
+                                 stopping_volume=stopping_volume, record_steps=record,
+                                 precision=p.get('precision', 'fp64'), device=self._device())
+            if run['stop'] == 'small':
+                print("Volume is to small")                             # FK_DTI.py:203-206 (sic)
+            volume = np.float64(run['volume'])
+            final_time = run['t_stop'] * dt if run['stop'] == 'volume' else stopping_time
+            final = _host.paste(grid.shape, run['state'], box)
+
+            result['initial_state'] = grid.upsample(initial)
+            result['final_state'] = grid.upsample(final)
+            result['final_time'] = final_time
+            result['final_volume'] = volume
+            result['stopping_criteria'] = 'volume' if volume >= stopping_volume else 'time'
+            result['time_series'] = (np.array([grid.upsample(_host.paste(grid.shape, s, box))
+                                               for s in run['snapshots']]) if record is not None else None)
+            result['Dw'] = Dw
+            result['rho'] = rho
+            result['success'] = True        # also after the "too small" exit, as in FK_DTI.py:229
+            self.last_loop_stats = {'steps_run': run['steps_run'], 'loop_ms': run.get('loop_ms'),
+                                    'voxels': int(np.prod(run['state'].shape))}
+        except Exception as e:              # FK_DTI.py:232-235
+            print(e)
+            result['error'] = str(e)
+            result['success'] = False
+        return result

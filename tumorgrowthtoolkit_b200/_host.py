@@ -1,0 +1,99 @@
+"""Host-side set-up and post-processing shared by the three solvers.
+
+These few lines of arithmetic define the CONTRACT of solve() (which grid the loop sees,
+how many steps of which dt it runs), not the hot path: resample, seed, step-count law,
+crop / restore.  Each function cites the reference lines whose behaviour it reproduces.
+"""
+import math
+
+import numpy as np
+from scipy.ndimage import zoom as _ndimage_zoom
+
+
+def resample_linear(a, factor):
+    """Trilinear resample with scipy.ndimage.zoom(order=1) semantics (FK/FK.py:150-151,
+    233-238).  The reference resamples on the host; so do we for now."""
+    return _ndimage_zoom(a, factor, order=1)
+
+
+class LowResGrid:
+    """The grid the time loop runs on (FK/FK.py:154-173)."""
+
+    def __init__(self, lowres_shape, fullres_shape, res_factor, dx_mm, dy_mm, dz_mm, pct):
+        self.shape = tuple(int(s) for s in lowres_shape[:3])
+        self.full_shape = tuple(int(s) for s in fullres_shape[:3])
+        # zoom factor that maps the low-res result back to the input grid  (FK.py:158)
+        self.up_factor = tuple(n / float(o) for n, o in zip(self.full_shape, self.shape))
+        self.h = (dx_mm / res_factor, dy_mm / res_factor, dz_mm / res_factor)  # FK.py:165-167
+        self.seed = tuple(int(p * n) for p, n in zip(pct, self.shape))         # FK.py:171-173
+
+    def upsample(self, a):
+        return np.array(resample_linear(a, self.up_factor))
+
+
+def seed_gaussian(grid, init_scale):
+    """Initial tumour: the clipped Gaussian of FK/FK.py:92-105 centred on the seed voxel
+    (FK.py:191-192): 250/(4*pi*5)^1.5 * exp(-r^2/20), r in mm/init_scale, <=0.1 -> 0, >1 -> 1."""
+    (nx, ny, nz), (dx, dy, dz), (sx, sy, sz) = grid.shape, grid.h, grid.seed
+    x = (np.arange(nx) - sx)[:, None, None] * dx / init_scale
+    y = (np.arange(ny) - sy)[None, :, None] * dy / init_scale
+    z = (np.arange(nz) - sz)[None, None, :] * dz / init_scale
+    spread = 5.0
+    g = 250 / np.power(4 * np.pi * spread, 3 / 2) * np.exp(
+        -(np.power(x, 2) + np.power(y, 2) + np.power(z, 2)) / (4 * spread))
+    g = np.where(g > 0.1, g, 0)
+    return np.where(g > 1, np.float64(1), g)
+
+
+def steps_and_dt(nt_float, stopping_time):
+    """`Nt` is a float: dt = T/Nt but ceil(Nt) steps are run (FK/FK.py:185-187)."""
+    dt = stopping_time / nt_float
+    return int(np.ceil(nt_float)), dt
+
+
+def record_schedule(nsteps, n_series):
+    """Step indices after which a snapshot is taken (FK/FK.py:208)."""
+    if n_series is None:
+        return None
+    return np.linspace(0, nsteps - 1, n_series, dtype=int)
+
+
+def bounding_box(mask, margin, shape):
+    """Bounding box of the true voxels of `mask`, grown by `margin` and clamped
+    (FK/FK.py:62-66).  Returns (min_coords, max_coords) as integer arrays."""
+    idx = np.argwhere(mask)
+    lo = np.maximum(idx.min(axis=0) - margin, 0)
+    hi = np.minimum(idx.max(axis=0) + margin + 1, shape)
+    return lo, hi
+
+
+def crop(a, box):
+    lo, hi = box
+    return a[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]]
+
+
+def paste(shape, a, box):
+    """Inverse of crop into a zero array (FK/FK.py:75-90)."""
+    out = np.zeros(shape)
+    lo, hi = box
+    out[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = a
+    return out
+
+
+def check_tissue_inputs(gm, wm, pct):
+    """Input validation of FK/FK.py:140-147 (raises AssertionError like the reference)."""
+    assert isinstance(gm, np.ndarray), "sGM must be a numpy array"
+    assert isinstance(wm, np.ndarray), "sWM must be a numpy array"
+    assert gm.ndim == 3, "sGM must be a 3D numpy array"
+    assert wm.ndim == 3, "sWM must be a 3D numpy array"
+    assert gm.shape == wm.shape
+    check_seed(pct)
+
+
+def check_seed(pct):
+    for name, v in zip(("NxT1_pct", "NyT1_pct", "NzT1_pct"), pct):
+        assert 0 <= v <= 1, f"{name} must be between 0 and 1"
+
+
+def is_finite_volume(v):
+    return v is not None and not (isinstance(v, float) and math.isnan(v))

@@ -1,0 +1,200 @@
+"""ctypes binding of libtgtk_b200.so (C ABI: include/tgtk_b200.h).
+
+There is no CPU implementation behind this module: if the shared library is missing, or no
+CUDA device is usable, every entry point raises.  Build the library with
+`python -c "import __graft_entry__ as g; g.build()"` or `make -C tumorgrowthtoolkit_b200/csrc`.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libtgtk_b200.so")
+
+MODEL_FK, MODEL_FK_2C, MODEL_DTI, MODEL_COEF6, MODEL_FK_FACES, MODEL_FK2C_COEF12 = 0, 1, 2, 3, 4, 5
+F64, F32 = 0, 1
+FIELD_U = FIELD_P = 0
+FIELD_N = 1
+FIELD_S = 2
+FIELD_WM, FIELD_GM = 10, 11
+FIELD_COEF0 = 20
+STOP_NONE, STOP_VOLUME, STOP_SMALL = 0, 1, 2
+
+_I64x3 = ctypes.c_int64 * 3
+
+
+class NativeError(RuntimeError):
+    """A call into libtgtk_b200 failed (CUDA error, bad argument, missing library)."""
+
+
+class Params(ctypes.Structure):
+    _fields_ = [("model", ctypes.c_int32), ("dtype", ctypes.c_int32),
+                ("X", ctypes.c_int32), ("Y", ctypes.c_int32), ("Z", ctypes.c_int32),
+                ("logical_or_faces", ctypes.c_int32),
+                ("h", ctypes.c_double * 3), ("dt", ctypes.c_double), ("rho", ctypes.c_double),
+                ("Dw", ctypes.c_double), ("ratio", ctypes.c_double), ("th_matter", ctypes.c_double),
+                ("th_necro", ctypes.c_double), ("Ds", ctypes.c_double), ("lambda_np", ctypes.c_double),
+                ("sigma_np", ctypes.c_double), ("lambda_s", ctypes.c_double),
+                ("stopping_volume", ctypes.c_double), ("small_volume", ctypes.c_double)]
+
+
+class Status(ctypes.Structure):
+    _fields_ = [("steps_run", ctypes.c_int32), ("stop_reason", ctypes.c_int32),
+                ("stop_step", ctypes.c_int32), ("snapshots", ctypes.c_int32),
+                ("last_volume", ctypes.c_double), ("loop_ms", ctypes.c_double),
+                ("kernel_launches", ctypes.c_int64)]
+
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library; raises NativeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(
+            f"{LIB_PATH} not found: the CUDA library has not been built "
+            "(run __graft_entry__.build() or `make -C tumorgrowthtoolkit_b200/csrc`). "
+            "There is no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    L.tgtk_last_error.restype = ctypes.c_char_p
+    L.tgtk_abi_version.restype = ctypes.c_int
+    vp, dp, ip = ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)
+    L.tgtk_device_count.argtypes = [ctypes.POINTER(ctypes.c_int)]
+    L.tgtk_sim_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(Params), ctypes.c_int, vp]
+    L.tgtk_sim_destroy.argtypes = [vp]
+    L.tgtk_sim_destroy.restype = None
+    L.tgtk_sim_upload.argtypes = [vp, ctypes.c_int, vp, _I64x3, ctypes.c_int]
+    L.tgtk_sim_download.argtypes = [vp, ctypes.c_int, vp, _I64x3]
+    L.tgtk_sim_prepare.argtypes = [vp]
+    L.tgtk_sim_run.argtypes = [vp, ctypes.c_int, ip, ctypes.c_int]
+    L.tgtk_sim_sync.argtypes = [vp, ctypes.POINTER(Status)]
+    L.tgtk_sim_volumes.argtypes = [vp, ctypes.c_int, ctypes.c_int, dp]
+    L.tgtk_sim_snapshot.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, _I64x3]
+    L.tgtk_sim_device_ptr.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong), _I64x3,
+                                      ctypes.POINTER(ctypes.c_int)]
+    if L.tgtk_abi_version() != 1:
+        raise NativeError("libtgtk_b200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise NativeError(lib().tgtk_last_error().decode("utf-8", "replace"))
+
+
+def device_count():
+    n = ctypes.c_int(0)
+    _check(lib().tgtk_device_count(ctypes.byref(n)))
+    return n.value
+
+
+def _as_f64(a):
+    """float64 view of `a` without copying when it already is float64 (any strides)."""
+    a = np.asarray(a)
+    if a.dtype != np.float64:
+        a = a.astype(np.float64)
+    return a
+
+
+def _strides(a):
+    return _I64x3(*[s // a.itemsize for s in a.strides])
+
+
+def make_params(model, dtype, shape, h, dt, rho=0.0, Dw=0.0, ratio=1.0, th_matter=0.0, th_necro=0.0,
+                Ds=0.0, lambda_np=0.0, sigma_np=0.0, lambda_s=0.0, stopping_volume=np.inf,
+                small_volume=0.0, logical_or_faces=0):
+    p = Params()
+    p.model, p.dtype = int(model), int(dtype)
+    p.X, p.Y, p.Z = (int(s) for s in shape)
+    p.logical_or_faces = int(logical_or_faces)
+    p.h[0], p.h[1], p.h[2] = (float(v) for v in h)
+    p.dt, p.rho, p.Dw, p.ratio, p.th_matter = float(dt), float(rho), float(Dw), float(ratio), float(th_matter)
+    p.th_necro, p.Ds, p.lambda_np = float(th_necro), float(Ds), float(lambda_np)
+    p.sigma_np, p.lambda_s = float(sigma_np), float(lambda_s)
+    p.stopping_volume, p.small_volume = float(stopping_volume), float(small_volume)
+    return p
+
+
+class Sim:
+    """One device-resident simulation (tgtk_sim*)."""
+
+    def __init__(self, params, device=0, stream=None):
+        self._h = ctypes.c_void_p()
+        self.params = params
+        self.shape = (params.X, params.Y, params.Z)
+        _check(lib().tgtk_sim_create(ctypes.byref(self._h), ctypes.byref(params), int(device),
+                                     ctypes.c_void_p(stream) if stream else None))
+
+    def close(self):
+        if self._h:
+            lib().tgtk_sim_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def upload(self, field, array, pinned=False):
+        a = _as_f64(array)
+        if a.shape != self.shape:
+            raise ValueError(f"array shape {a.shape} does not match the simulation box {self.shape}")
+        _check(lib().tgtk_sim_upload(self._h, int(field), a.ctypes.data_as(ctypes.c_void_p), _strides(a),
+                                     1 if pinned else 0))
+        # uploads from pageable memory have completed on return; pinned ones are asynchronous and
+        # the caller keeps `array` alive until the next sync()
+
+    def prepare(self):
+        _check(lib().tgtk_sim_prepare(self._h))
+
+    def run(self, nsteps, record_steps=None):
+        if record_steps is None or len(record_steps) == 0:
+            _check(lib().tgtk_sim_run(self._h, int(nsteps), None, 0))
+        else:
+            rec = np.ascontiguousarray(np.unique(np.asarray(record_steps)), dtype=np.int32)
+            _check(lib().tgtk_sim_run(self._h, int(nsteps),
+                                      rec.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), int(rec.size)))
+
+    def sync(self):
+        st = Status()
+        _check(lib().tgtk_sim_sync(self._h, ctypes.byref(st)))
+        return st
+
+    def download(self, field, out=None):
+        if out is None:
+            out = np.empty(self.shape, dtype=np.float64)
+        _check(lib().tgtk_sim_download(self._h, int(field), out.ctypes.data_as(ctypes.c_void_p), _strides(out)))
+        return out
+
+    def snapshot(self, index, field, out=None):
+        if out is None:
+            out = np.empty(self.shape, dtype=np.float64)
+        _check(lib().tgtk_sim_snapshot(self._h, int(index), int(field), out.ctypes.data_as(ctypes.c_void_p),
+                                       _strides(out)))
+        return out
+
+    def volumes(self, first, count):
+        out = np.empty(int(count), dtype=np.float64)
+        if count:
+            _check(lib().tgtk_sim_volumes(self._h, int(first), int(count),
+                                          out.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+        return out
+
+    def device_ptr(self, field):
+        ptr = ctypes.c_ulonglong(0)
+        pitches = _I64x3()
+        es = ctypes.c_int(0)
+        _check(lib().tgtk_sim_device_ptr(self._h, int(field), ctypes.byref(ptr), pitches, ctypes.byref(es)))
+        return ptr.value, tuple(pitches), es.value

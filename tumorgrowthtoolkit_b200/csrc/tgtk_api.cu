@@ -1,0 +1,642 @@
+// C ABI of libtgtk_b200 (see include/tgtk_b200.h).  Host-side driver of the time loop:
+// device memory, uploads/downloads, launch sequencing, snapshots, status.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/tgtk_b200.h"
+#include "tgtk_common.cuh"
+#include "tgtk_kernels_v1.cuh"
+
+using namespace tgtk;
+
+static thread_local std::string g_err;
+
+static int fail(const char *what, const char *detail)
+{
+    g_err = std::string(what) + ": " + detail;
+    return 1;
+}
+
+#define CU(call)                                                         \
+    do {                                                                 \
+        cudaError_t e__ = (call);                                        \
+        if (e__ != cudaSuccess) return fail(#call, cudaGetErrorString(e__)); \
+    } while (0)
+
+struct tgtk_sim {
+    tgtk_params p;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    size_t n = 0;          // voxels
+    size_t elem = 8;       // sizeof state type
+    int64_t sx = 0, sy = 0;
+    int nfields = 1, ncoef = 0;
+    void *state[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    void *coef[12] = {nullptr};
+    double *stage = nullptr;  // dense float64 staging for uploads / downloads
+    double *wm = nullptr, *gm = nullptr, *pc = nullptr, *pn = nullptr;
+    int faces_what = 0;  // tgtk_faces_host: 0 D_minus, 1 WM_tilda, 2 GM_tilda
+    Ctrl *ctrl = nullptr;
+    Ctrl *ctrl_host = nullptr;  // pinned mirror
+    double *partials = nullptr;
+    double *volumes = nullptr;
+    int volumes_cap = 0;
+    dim3 grid, block;
+    unsigned nblocks = 0;
+    int t_enqueued = 0;
+    bool prepared = false;
+    int kernel_variant = 0;
+    std::vector<void *> snaps;     // one allocation per snapshot: nfields * n * elem
+    std::vector<int> snap_steps;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    int64_t launches = 0;
+};
+
+// ------------------------------------------------------------------------------------------
+// layout conversion and coefficient set-up kernels
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_kernel(const double *__restrict__ src, T *__restrict__ dst, int X, int Y, int Z,
+                            int64_t sx, int64_t sy)
+{
+    const int64_t n = (int64_t)X * Y * Z;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(q % Z);
+        const int64_t r = q / Z;
+        const int j = (int)(r % Y);
+        const int i = (int)(r / Y);
+        dst[i * sx + j * sy + k] = (T)src[q];
+    }
+}
+
+template <typename T>
+__global__ void unpack_kernel(const T *__restrict__ src, double *__restrict__ dst, int X, int Y, int Z,
+                              int64_t sx, int64_t sy)
+{
+    const int64_t n = (int64_t)X * Y * Z;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(q % Z);
+        const int64_t r = q / Z;
+        const int j = (int)(r % Y);
+        const int i = (int)(r / Y);
+        dst[q] = (double)src[i * sx + j * sy + k];
+    }
+}
+
+// k(c) and b(c) of the compact FK / FK_2c kernels, evaluated in float64 from the float64
+// tissue maps and rounded once to the state type.
+template <typename T>
+__global__ void prep_compact_kernel(const double *__restrict__ wm, const double *__restrict__ gm, T *__restrict__ kc,
+                                    T *__restrict__ bc, double th, double ratio, int X, int Y, int Z, int64_t sx,
+                                    int64_t sy)
+{
+    const int64_t n = (int64_t)X * Y * Z;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(q % Z);
+        const int64_t r = q / Z;
+        const int j = (int)(r % Y);
+        const int i = (int)(r / Y);
+        const double w = wm[q], g = gm[q];
+        const bool tissue = (w + g >= th);
+        const int64_t d = i * sx + j * sy + k;
+        kc[d] = tissue ? (T)(0.5 * (w + g / ratio)) : -Big<T>::v;
+        if (bc) bc[d] = tissue ? (T)(0.5 * (w + g)) : -Big<T>::v;
+    }
+}
+
+// D_minus_{x,y,z} in the reference's own rounding order (FK/FK.py:12-26): used by the
+// bit-exact FACES model.  logical_or: numpy bool semantics of '+' (SURVEY.md 7).
+template <typename T>
+__global__ void prep_faces_kernel(const double *__restrict__ wm, const double *__restrict__ gm,
+                                  const double *__restrict__ pc, const double *__restrict__ pn, T *__restrict__ fx,
+                                  T *__restrict__ fy, T *__restrict__ fz, double th, double th_necro, double Dw,
+                                  double ratio, int logical_or, int what, int X, int Y, int Z, int64_t sx, int64_t sy)
+{
+    const int64_t n = (int64_t)X * Y * Z;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(q % Z);
+        const int64_t r = q / Z;
+        const int j = (int)(r % Y);
+        const int i = (int)(r / Y);
+        const int ip = (i + 1 == X) ? 0 : i + 1, jp = (j + 1 == Y) ? 0 : j + 1, kp = (k + 1 == Z) ? 0 : k + 1;
+        const int64_t nb[3] = {((int64_t)ip * Y + j) * Z + k, ((int64_t)i * Y + jp) * Z + k, ((int64_t)i * Y + j) * Z + kp};
+        T *out[3] = {fx, fy, fz};
+        const double w = wm[q], g = gm[q];
+        auto plus = [&](double a, double b) {
+            return logical_or ? ((a != 0.0 || b != 0.0) ? 1.0 : 0.0) : __dadd_rn(a, b);
+        };
+        // FK_2c/FK_2c.py:13-15: both ends of the face need (P+N) <= th_necro
+        const bool here = plus(w, g) >= th && (!pc || __dadd_rn(pc[q], pn[q]) <= th_necro);
+        for (int a = 0; a < 3; ++a) {
+            const double w2 = wm[nb[a]], g2 = gm[nb[a]];
+            double wt = 0.0, gt = 0.0;
+            if (here && plus(w2, g2) >= th && (!pc || __dadd_rn(pc[nb[a]], pn[nb[a]]) <= th_necro)) {
+                wt = plus(w2, w) / 2;
+                gt = plus(g2, g) / 2;
+            }
+            const double v = (what == 1) ? wt : (what == 2) ? gt : __dmul_rn(Dw, __dadd_rn(wt, __ddiv_rn(gt, ratio)));
+            out[a][i * sx + j * sy + k] = (T)v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+static inline int grid_1d(size_t n) { return (int)std::min<size_t>((n + 255) / 256, 148 * 16); }
+
+template <typename T> static void fill_args(const tgtk_sim *s, StepArgs<T> &a)
+{
+    const tgtk_params &p = s->p;
+    a.X = p.X; a.Y = p.Y; a.Z = p.Z;
+    a.sx = s->sx; a.sy = s->sy;
+    for (int b = 0; b < 2; ++b)
+        for (int f = 0; f < 3; ++f) a.buf[b][f] = (T *)s->state[b][f];
+    for (int c = 0; c < 12; ++c) a.coef[c] = (const T *)s->coef[c];
+    const double ix = 1.0 / (p.h[0] * p.h[0]), iy = 1.0 / (p.h[1] * p.h[1]), iz = 1.0 / (p.h[2] * p.h[2]);
+    const bool fold = (p.model == TGTK_MODEL_FK || p.model == TGTK_MODEL_FK_2C);
+    a.cx = (T)(fold ? p.Dw * ix : ix);
+    a.cy = (T)(fold ? p.Dw * iy : iy);
+    a.cz = (T)(fold ? p.Dw * iz : iz);
+    a.ex = (T)(p.Ds * ix); a.ey = (T)(p.Ds * iy); a.ez = (T)(p.Ds * iz);
+    a.dt = (T)p.dt; a.rho = (T)p.rho;
+    a.th_necro = (T)p.th_necro; a.lambda_np = (T)p.lambda_np; a.sigma_np = (T)p.sigma_np; a.lambda_s = (T)p.lambda_s;
+    a.vol_scale_p = p.h[0] * p.h[1] * p.h[2];
+    a.vol_scale_n = 1.0;
+    a.stop_volume = p.stopping_volume;
+    a.small_volume = p.small_volume;
+    a.ctrl = s->ctrl;
+    a.partials = s->partials;
+    a.volumes = s->volumes;
+    a.volumes_cap = s->volumes_cap;
+}
+
+template <typename T> static cudaError_t launch_step(tgtk_sim *s)
+{
+    StepArgs<T> a;
+    fill_args(s, a);
+    switch (s->p.model) {
+    case TGTK_MODEL_FK: fk_step_v1<T><<<s->grid, s->block, 0, s->stream>>>(a); break;
+    case TGTK_MODEL_FK_2C: fk2c_step_v1<T><<<s->grid, s->block, 0, s->stream>>>(a); break;
+    case TGTK_MODEL_DTI: coef_step_v1<T, 2><<<s->grid, s->block, 0, s->stream>>>(a); break;
+    case TGTK_MODEL_COEF6: coef_step_v1<T, 0><<<s->grid, s->block, 0, s->stream>>>(a); break;
+    case TGTK_MODEL_FK_FACES: coef_step_v1<T, 1><<<s->grid, s->block, 0, s->stream>>>(a); break;
+    case TGTK_MODEL_FK2C_COEF12: fk2c_coef_step_v1<T><<<s->grid, s->block, 0, s->stream>>>(a); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+static int ensure_volumes(tgtk_sim *s, int need)
+{
+    if (need <= s->volumes_cap) return 0;
+    int cap = std::max(need, std::max(1024, s->volumes_cap * 2));
+    double *nv = nullptr;
+    CU(cudaMalloc(&nv, sizeof(double) * cap));
+    CU(cudaMemsetAsync(nv, 0, sizeof(double) * cap, s->stream));
+    if (s->volumes) {
+        CU(cudaMemcpyAsync(nv, s->volumes, sizeof(double) * s->volumes_cap, cudaMemcpyDeviceToDevice, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        CU(cudaFree(s->volumes));
+    }
+    s->volumes = nv;
+    s->volumes_cap = cap;
+    return 0;
+}
+
+static void *field_ptr(tgtk_sim *s, int field, int which_buf)
+{
+    if (field >= 0 && field < s->nfields) return s->state[which_buf][field];
+    if (field >= TGTK_FIELD_COEF0 && field < TGTK_FIELD_COEF0 + 12) return s->coef[field - TGTK_FIELD_COEF0];
+    return nullptr;
+}
+
+static bool dense(const tgtk_sim *s, const int64_t st[3])
+{
+    return st[2] == 1 && st[1] == s->p.Z && st[0] == (int64_t)s->p.Y * s->p.Z;
+}
+
+// host (float64, strided) <-> dense device staging
+static int copy_host_stage(tgtk_sim *s, double *host, const int64_t st[3], bool to_device)
+{
+    const tgtk_params &p = s->p;
+    const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    if (dense(s, st)) {
+        if (to_device) CU(cudaMemcpyAsync(s->stage, host, s->n * 8, kind, s->stream));
+        else CU(cudaMemcpyAsync(host, s->stage, s->n * 8, kind, s->stream));
+        return 0;
+    }
+    if (st[2] == 1 && st[1] >= p.Z && st[0] % st[1] == 0 && st[0] / st[1] >= p.Y) {
+        cudaMemcpy3DParms c;
+        memset(&c, 0, sizeof(c));
+        cudaPitchedPtr hp = make_cudaPitchedPtr(host, (size_t)st[1] * 8, (size_t)p.Z * 8, (size_t)(st[0] / st[1]));
+        cudaPitchedPtr dp = make_cudaPitchedPtr(s->stage, (size_t)p.Z * 8, (size_t)p.Z * 8, (size_t)p.Y);
+        c.srcPtr = to_device ? hp : dp;
+        c.dstPtr = to_device ? dp : hp;
+        c.extent = make_cudaExtent((size_t)p.Z * 8, (size_t)p.Y, (size_t)p.X);
+        c.kind = kind;
+        CU(cudaMemcpy3DAsync(&c, s->stream));
+        return 0;
+    }
+    // arbitrary strides: gather / scatter on the host
+    std::vector<double> tmp(s->n);
+    if (to_device) {
+        size_t q = 0;
+        for (int i = 0; i < p.X; ++i)
+            for (int j = 0; j < p.Y; ++j)
+                for (int k = 0; k < p.Z; ++k) tmp[q++] = host[i * st[0] + j * st[1] + k * st[2]];
+        CU(cudaMemcpyAsync(s->stage, tmp.data(), s->n * 8, kind, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    } else {
+        CU(cudaMemcpyAsync(tmp.data(), s->stage, s->n * 8, kind, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        size_t q = 0;
+        for (int i = 0; i < p.X; ++i)
+            for (int j = 0; j < p.Y; ++j)
+                for (int k = 0; k < p.Z; ++k) host[i * st[0] + j * st[1] + k * st[2]] = tmp[q++];
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int tgtk_abi_version(void) { return TGTK_ABI_VERSION; }
+
+const char *tgtk_last_error(void) { return g_err.c_str(); }
+
+int tgtk_device_count(int *count)
+{
+    CU(cudaGetDeviceCount(count));
+    return 0;
+}
+
+int tgtk_sim_create(tgtk_sim **out, const tgtk_params *params, int device, void *stream)
+{
+    if (!out || !params) return fail("tgtk_sim_create", "null argument");
+    const tgtk_params &p = *params;
+    if (p.X < 1 || p.Y < 1 || p.Z < 1) return fail("tgtk_sim_create", "empty box");
+    if (p.model < 0 || p.model > TGTK_MODEL_FK2C_COEF12) return fail("tgtk_sim_create", "unknown model");
+    if (p.dtype != TGTK_F64 && p.dtype != TGTK_F32) return fail("tgtk_sim_create", "unknown dtype");
+    if (!(p.h[0] > 0 && p.h[1] > 0 && p.h[2] > 0)) return fail("tgtk_sim_create", "non-positive grid spacing");
+    CU(cudaSetDevice(device));
+    tgtk_sim *s = new (std::nothrow) tgtk_sim();
+    if (!s) return fail("tgtk_sim_create", "out of host memory");
+    s->p = p;
+    s->device = device;
+    if (stream) {
+        s->stream = (cudaStream_t)stream;
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete s; return fail("cudaStreamCreate", cudaGetErrorString(e)); }
+        s->own_stream = true;
+    }
+    s->n = (size_t)p.X * p.Y * p.Z;
+    s->elem = (p.dtype == TGTK_F64) ? 8 : 4;
+    s->sy = p.Z;
+    s->sx = (int64_t)p.Y * p.Z;
+    s->nfields = (p.model == TGTK_MODEL_FK_2C || p.model == TGTK_MODEL_FK2C_COEF12) ? 3 : 1;
+    switch (p.model) {
+    case TGTK_MODEL_FK: s->ncoef = 1; break;
+    case TGTK_MODEL_FK_2C: s->ncoef = 2; break;
+    case TGTK_MODEL_DTI: s->ncoef = 3; break;
+    case TGTK_MODEL_COEF6: s->ncoef = 6; break;
+    case TGTK_MODEL_FK_FACES: s->ncoef = 3; break;
+    case TGTK_MODEL_FK2C_COEF12: s->ncoef = 12; break;
+    }
+    s->block = dim3(32, 4, 2);
+    s->grid = dim3((p.Z + 31) / 32, (p.Y + 3) / 4, (p.X + 1) / 2);
+    s->nblocks = s->grid.x * s->grid.y * s->grid.z;
+    *out = s;  // from here on tgtk_sim_destroy cleans up on failure
+    const size_t bytes = (size_t)p.X * s->sx * s->elem;
+    for (int b = 0; b < 2; ++b)
+        for (int f = 0; f < s->nfields; ++f) {
+            CU(cudaMalloc(&s->state[b][f], bytes));
+            CU(cudaMemsetAsync(s->state[b][f], 0, bytes, s->stream));
+        }
+    for (int c = 0; c < s->ncoef; ++c) {
+        CU(cudaMalloc(&s->coef[c], bytes));
+        CU(cudaMemsetAsync(s->coef[c], 0, bytes, s->stream));
+    }
+    CU(cudaMalloc(&s->stage, s->n * 8));
+    CU(cudaMalloc(&s->ctrl, sizeof(Ctrl)));
+    CU(cudaMallocHost(&s->ctrl_host, sizeof(Ctrl)));
+    CU(cudaMalloc(&s->partials, sizeof(double) * 2 * s->nblocks));
+    CU(cudaEventCreate(&s->ev0));
+    CU(cudaEventCreate(&s->ev1));
+    Ctrl init = {0, 0, -1, 0u, 0.0};
+    *s->ctrl_host = init;
+    CU(cudaMemcpyAsync(s->ctrl, s->ctrl_host, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
+    if (ensure_volumes(s, 1024)) return 1;
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+void tgtk_sim_destroy(tgtk_sim *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (int b = 0; b < 2; ++b)
+        for (int f = 0; f < 3; ++f) cudaFree(s->state[b][f]);
+    for (int c = 0; c < 12; ++c) cudaFree(s->coef[c]);
+    for (void *q : s->snaps) cudaFree(q);
+    cudaFree(s->stage);
+    cudaFree(s->wm);
+    cudaFree(s->gm);
+    cudaFree(s->pc);
+    cudaFree(s->pn);
+    cudaFree(s->ctrl);
+    cudaFree(s->partials);
+    cudaFree(s->volumes);
+    if (s->ctrl_host) cudaFreeHost(s->ctrl_host);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int tgtk_sim_upload(tgtk_sim *s, int field, const double *host, const int64_t strides[3], int pinned)
+{
+    (void)pinned;
+    if (!s || !host || !strides) return fail("tgtk_sim_upload", "null argument");
+    CU(cudaSetDevice(s->device));
+    const tgtk_params &p = s->p;
+    if (field >= TGTK_FIELD_WM && field <= TGTK_FIELD_NC) {
+        if (p.model != TGTK_MODEL_FK && p.model != TGTK_MODEL_FK_2C && p.model != TGTK_MODEL_FK_FACES)
+            return fail("tgtk_sim_upload", "model takes no tissue maps");
+        double **dst = (field == TGTK_FIELD_WM) ? &s->wm : (field == TGTK_FIELD_GM) ? &s->gm
+                       : (field == TGTK_FIELD_PC) ? &s->pc : &s->pn;
+        if (!*dst) CU(cudaMalloc(dst, s->n * 8));
+        if (copy_host_stage(s, const_cast<double *>(host), strides, true)) return 1;
+        CU(cudaMemcpyAsync(*dst, s->stage, s->n * 8, cudaMemcpyDeviceToDevice, s->stream));
+        s->prepared = false;
+        return 0;
+    }
+    const int cur = s->t_enqueued & 1;
+    void *dst = field_ptr(s, field, cur);
+    if (!dst) return fail("tgtk_sim_upload", "field not present in this model");
+    if (field >= TGTK_FIELD_COEF0 && p.model != TGTK_MODEL_DTI && p.model != TGTK_MODEL_COEF6 &&
+        p.model != TGTK_MODEL_FK2C_COEF12)
+        return fail("tgtk_sim_upload", "coefficient arrays of this model are built by tgtk_sim_prepare");
+    if (copy_host_stage(s, const_cast<double *>(host), strides, true)) return 1;
+    if (p.dtype == TGTK_F64)
+        pack_kernel<double><<<grid_1d(s->n), 256, 0, s->stream>>>(s->stage, (double *)dst, p.X, p.Y, p.Z, s->sx, s->sy);
+    else
+        pack_kernel<float><<<grid_1d(s->n), 256, 0, s->stream>>>(s->stage, (float *)dst, p.X, p.Y, p.Z, s->sx, s->sy);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int download_ptr(tgtk_sim *s, const void *src, double *host, const int64_t strides[3])
+{
+    const tgtk_params &p = s->p;
+    if (p.dtype == TGTK_F64)
+        unpack_kernel<double><<<grid_1d(s->n), 256, 0, s->stream>>>((const double *)src, s->stage, p.X, p.Y, p.Z, s->sx, s->sy);
+    else
+        unpack_kernel<float><<<grid_1d(s->n), 256, 0, s->stream>>>((const float *)src, s->stage, p.X, p.Y, p.Z, s->sx, s->sy);
+    CU(cudaGetLastError());
+    if (copy_host_stage(s, host, strides, false)) return 1;
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+// index of the buffer that holds the current state: step t writes buf[(t+1)&1]
+static int current_buf(tgtk_sim *s, int *steps_run)
+{
+    const Ctrl &c = *s->ctrl_host;
+    if (steps_run) *steps_run = c.t;
+    return c.t & 1;
+}
+
+static int fetch_ctrl(tgtk_sim *s)
+{
+    CU(cudaMemcpyAsync(s->ctrl_host, s->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int tgtk_sim_download(tgtk_sim *s, int field, double *host, const int64_t strides[3])
+{
+    if (!s || !host || !strides) return fail("tgtk_sim_download", "null argument");
+    CU(cudaSetDevice(s->device));
+    if (fetch_ctrl(s)) return 1;
+    void *src = field_ptr(s, field, current_buf(s, nullptr));
+    if (!src) return fail("tgtk_sim_download", "field not present in this model");
+    return download_ptr(s, src, host, strides);
+}
+
+int tgtk_sim_prepare(tgtk_sim *s)
+{
+    if (!s) return fail("tgtk_sim_prepare", "null argument");
+    CU(cudaSetDevice(s->device));
+    const tgtk_params &p = s->p;
+    const bool tissue_model = (p.model == TGTK_MODEL_FK || p.model == TGTK_MODEL_FK_2C || p.model == TGTK_MODEL_FK_FACES);
+    if (tissue_model) {
+        if (!s->wm || !s->gm) return fail("tgtk_sim_prepare", "upload TGTK_FIELD_WM and TGTK_FIELD_GM first");
+        const int g = grid_1d(s->n);
+        if (p.model == TGTK_MODEL_FK_FACES) {
+            if (p.dtype == TGTK_F64)
+                prep_faces_kernel<double><<<g, 256, 0, s->stream>>>(s->wm, s->gm, s->pc, s->pn, (double *)s->coef[0],
+                                                                   (double *)s->coef[1], (double *)s->coef[2], p.th_matter,
+                                                                   p.th_necro, p.Dw, p.ratio, p.logical_or_faces,
+                                                                   s->faces_what, p.X, p.Y, p.Z, s->sx, s->sy);
+            else
+                prep_faces_kernel<float><<<g, 256, 0, s->stream>>>(s->wm, s->gm, s->pc, s->pn, (float *)s->coef[0],
+                                                                  (float *)s->coef[1], (float *)s->coef[2], p.th_matter,
+                                                                  p.th_necro, p.Dw, p.ratio, p.logical_or_faces,
+                                                                  s->faces_what, p.X, p.Y, p.Z, s->sx, s->sy);
+        } else {
+            if (p.dtype == TGTK_F64)
+                prep_compact_kernel<double><<<g, 256, 0, s->stream>>>(s->wm, s->gm, (double *)s->coef[0], (double *)s->coef[1],
+                                                                     p.th_matter, p.ratio, p.X, p.Y, p.Z, s->sx, s->sy);
+            else
+                prep_compact_kernel<float><<<g, 256, 0, s->stream>>>(s->wm, s->gm, (float *)s->coef[0], (float *)s->coef[1],
+                                                                    p.th_matter, p.ratio, p.X, p.Y, p.Z, s->sx, s->sy);
+        }
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(s->stream));
+        CU(cudaFree(s->wm));
+        CU(cudaFree(s->gm));
+        CU(cudaFree(s->pc));
+        CU(cudaFree(s->pn));
+        s->wm = s->gm = s->pc = s->pn = nullptr;
+    }
+    s->prepared = true;
+    return 0;
+}
+
+int tgtk_sim_run(tgtk_sim *s, int nsteps, const int32_t *record_steps, int nrecord)
+{
+    if (!s) return fail("tgtk_sim_run", "null argument");
+    if (!s->prepared) return fail("tgtk_sim_run", "call tgtk_sim_prepare first");
+    if (nsteps < 0) return fail("tgtk_sim_run", "negative step count");
+    CU(cudaSetDevice(s->device));
+    if (ensure_volumes(s, s->t_enqueued + nsteps)) return 1;
+    const size_t bytes = (size_t)s->p.X * s->sx * s->elem;
+    int r = 0;
+    while (r < nrecord && record_steps[r] < s->t_enqueued) ++r;
+    CU(cudaEventRecord(s->ev0, s->stream));
+    for (int q = 0; q < nsteps; ++q) {
+        const int t = s->t_enqueued;
+        cudaError_t e = (s->p.dtype == TGTK_F64) ? launch_step<double>(s) : launch_step<float>(s);
+        if (e != cudaSuccess) return fail("step launch", cudaGetErrorString(e));
+        ++s->launches;
+        ++s->t_enqueued;
+        bool rec = false;
+        while (r < nrecord && record_steps[r] == t) { rec = true; ++r; }
+        if (rec) {
+            // state after step t lives in buf[(t+1)&1]; FK/FK.py:221-223
+            void *arena = nullptr;
+            CU(cudaMalloc(&arena, bytes * s->nfields));
+            for (int f = 0; f < s->nfields; ++f)
+                CU(cudaMemcpyAsync((char *)arena + bytes * f, s->state[(t + 1) & 1][f], bytes, cudaMemcpyDeviceToDevice,
+                                   s->stream));
+            s->snaps.push_back(arena);
+            s->snap_steps.push_back(t);
+        }
+    }
+    CU(cudaEventRecord(s->ev1, s->stream));
+    s->timed = true;
+    return 0;
+}
+
+int tgtk_sim_sync(tgtk_sim *s, tgtk_status *st)
+{
+    if (!s) return fail("tgtk_sim_sync", "null argument");
+    CU(cudaSetDevice(s->device));
+    if (fetch_ctrl(s)) return 1;
+    if (st) {
+        const Ctrl &c = *s->ctrl_host;
+        st->steps_run = c.t;
+        st->stop_reason = c.stop_reason;
+        st->stop_step = c.stop_step;
+        st->last_volume = c.last_volume;
+        int valid = 0;
+        // a snapshot of step t is valid only if the loop got past step t's stop test
+        for (int q : s->snap_steps)
+            if (q < c.t && !(c.stop_reason != 0 && q >= c.stop_step)) ++valid;
+        st->snapshots = valid;
+        float ms = 0.f;
+        if (s->timed) CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        st->loop_ms = ms;
+        st->kernel_launches = s->launches;
+    }
+    return 0;
+}
+
+int tgtk_sim_volumes(tgtk_sim *s, int first, int count, double *out)
+{
+    if (!s || !out) return fail("tgtk_sim_volumes", "null argument");
+    if (first < 0 || count < 0 || first + count > s->volumes_cap) return fail("tgtk_sim_volumes", "range outside the log");
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpyAsync(out, s->volumes + first, sizeof(double) * count, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int tgtk_sim_snapshot(tgtk_sim *s, int index, int field, double *host, const int64_t strides[3])
+{
+    if (!s || !host || !strides) return fail("tgtk_sim_snapshot", "null argument");
+    if (index < 0 || index >= (int)s->snaps.size()) return fail("tgtk_sim_snapshot", "no such snapshot");
+    if (field < 0 || field >= s->nfields) return fail("tgtk_sim_snapshot", "no such field");
+    CU(cudaSetDevice(s->device));
+    const size_t bytes = (size_t)s->p.X * s->sx * s->elem;
+    return download_ptr(s, (char *)s->snaps[index] + bytes * field, host, strides);
+}
+
+int tgtk_sim_device_ptr(tgtk_sim *s, int field, unsigned long long *ptr, int64_t pitches[3], int *elem_size)
+{
+    if (!s || !ptr) return fail("tgtk_sim_device_ptr", "null argument");
+    CU(cudaSetDevice(s->device));
+    if (fetch_ctrl(s)) return 1;
+    void *q = field_ptr(s, field, current_buf(s, nullptr));
+    if (!q) return fail("tgtk_sim_device_ptr", "field not present in this model");
+    *ptr = (unsigned long long)(uintptr_t)q;
+    if (pitches) { pitches[0] = s->sx; pitches[1] = s->sy; pitches[2] = 1; }
+    if (elem_size) *elem_size = (int)s->elem;
+    return 0;
+}
+
+int tgtk_fk_update_host(const tgtk_params *params, int device, double *A, const int64_t a_strides[3],
+                        const double *const coef[6], const int64_t coef_strides[6][3])
+{
+    if (!params || !A || !coef) return fail("tgtk_fk_update_host", "null argument");
+    tgtk_params p = *params;
+    p.model = TGTK_MODEL_COEF6;
+    p.stopping_volume = INFINITY;
+    p.small_volume = 0.0;
+    tgtk_sim *s = nullptr;
+    int rc = tgtk_sim_create(&s, &p, device, nullptr);
+    if (!rc) rc = tgtk_sim_upload(s, TGTK_FIELD_U, A, a_strides, 0);
+    for (int c = 0; c < 6 && !rc; ++c) rc = tgtk_sim_upload(s, TGTK_FIELD_COEF0 + c, coef[c], coef_strides[c], 0);
+    if (!rc) rc = tgtk_sim_prepare(s);
+    if (!rc) rc = tgtk_sim_run(s, 1, nullptr, 0);
+    if (!rc) rc = tgtk_sim_download(s, TGTK_FIELD_U, A, a_strides);
+    tgtk_sim_destroy(s);
+    return rc;
+}
+
+int tgtk_fk2c_update_host(const tgtk_params *params, int device, double *P, const int64_t p_strides[3],
+                          double *N, const int64_t n_strides[3], double *S, const int64_t s_strides[3],
+                          const double *const D[6], const int64_t d_strides[6][3],
+                          const double *const Ds[6], const int64_t ds_strides[6][3])
+{
+    if (!params || !P || !N || !S || !D || !Ds) return fail("tgtk_fk2c_update_host", "null argument");
+    tgtk_params p = *params;
+    p.model = TGTK_MODEL_FK2C_COEF12;
+    p.stopping_volume = INFINITY;
+    p.small_volume = 0.0;
+    tgtk_sim *s = nullptr;
+    int rc = tgtk_sim_create(&s, &p, device, nullptr);
+    if (!rc) rc = tgtk_sim_upload(s, TGTK_FIELD_P, P, p_strides, 0);
+    if (!rc) rc = tgtk_sim_upload(s, TGTK_FIELD_N, N, n_strides, 0);
+    if (!rc) rc = tgtk_sim_upload(s, TGTK_FIELD_S, S, s_strides, 0);
+    for (int c = 0; c < 6 && !rc; ++c) rc = tgtk_sim_upload(s, TGTK_FIELD_COEF0 + c, D[c], d_strides[c], 0);
+    for (int c = 0; c < 6 && !rc; ++c) rc = tgtk_sim_upload(s, TGTK_FIELD_COEF0 + 6 + c, Ds[c], ds_strides[c], 0);
+    if (!rc) rc = tgtk_sim_prepare(s);
+    if (!rc) rc = tgtk_sim_run(s, 1, nullptr, 0);
+    if (!rc) rc = tgtk_sim_download(s, TGTK_FIELD_P, P, p_strides);
+    if (!rc) rc = tgtk_sim_download(s, TGTK_FIELD_N, N, n_strides);
+    if (!rc) rc = tgtk_sim_download(s, TGTK_FIELD_S, S, s_strides);
+    tgtk_sim_destroy(s);
+    return rc;
+}
+
+int tgtk_faces_host(int device, int X, int Y, int Z, const double *wm, const int64_t wm_strides[3],
+                    const double *gm, const int64_t gm_strides[3], const double *P, const int64_t p_strides[3],
+                    const double *N, const int64_t n_strides[3], double th, double th_necro, double Dw,
+                    double ratio, int logical_or, int what, double *out_x, double *out_y, double *out_z)
+{
+    if (!wm || !gm || !out_x || !out_y || !out_z) return fail("tgtk_faces_host", "null argument");
+    if ((P == nullptr) != (N == nullptr)) return fail("tgtk_faces_host", "P and N must be given together");
+    tgtk_params p;
+    memset(&p, 0, sizeof(p));
+    p.model = TGTK_MODEL_FK_FACES;
+    p.dtype = TGTK_F64;
+    p.X = X; p.Y = Y; p.Z = Z;
+    p.logical_or_faces = logical_or;
+    p.h[0] = p.h[1] = p.h[2] = 1.0;
+    p.Dw = Dw; p.ratio = ratio; p.th_matter = th; p.th_necro = th_necro;
+    p.stopping_volume = INFINITY;
+    tgtk_sim *s = nullptr;
+    int rc = tgtk_sim_create(&s, &p, device, nullptr);
+    if (!rc) s->faces_what = what;
+    if (!rc) rc = tgtk_sim_upload(s, TGTK_FIELD_WM, wm, wm_strides, 0);
+    if (!rc) rc = tgtk_sim_upload(s, TGTK_FIELD_GM, gm, gm_strides, 0);
+    if (!rc && P) rc = tgtk_sim_upload(s, TGTK_FIELD_PC, P, p_strides, 0);
+    if (!rc && N) rc = tgtk_sim_upload(s, TGTK_FIELD_NC, N, n_strides, 0);
+    if (!rc) rc = tgtk_sim_prepare(s);
+    const int64_t dense_st[3] = {(int64_t)Y * Z, Z, 1};
+    double *outs[3] = {out_x, out_y, out_z};
+    for (int a = 0; a < 3 && !rc; ++a) rc = tgtk_sim_download(s, TGTK_FIELD_COEF0 + a, outs[a], dense_st);
+    tgtk_sim_destroy(s);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,155 @@
+// Shared device-side definitions of libtgtk_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tgtk {
+
+// Sentinel for "no flux through any face of this voxel": face = max(k(c) + k(c'), 0), so one
+// closed end drives the sum far below zero and the face coefficient to exactly 0.
+template <typename T> struct Big;
+template <> struct Big<double> { static constexpr double v = 1.0e300; };
+template <> struct Big<float> { static constexpr float v = 1.0e30f; };
+
+// Device-resident loop control: lets identical launches be enqueued back to back (and
+// captured in CUDA graphs) while the stop test of the reference loops
+// (FK/FK.py:216-218, FK_DTI/FK_DTI.py:199-206) is evaluated on the device after every step.
+struct Ctrl {
+    int t;            // index of the next step to execute
+    int stop_reason;  // tgtk_stop; non-zero freezes the state (later launches return at once)
+    int stop_step;    // step index that tripped the test, -1 if none
+    unsigned ticket;  // last-block-done counter of the running launch
+    double last_volume;
+};
+
+// Everything a step kernel needs; passed by value.
+template <typename T> struct StepArgs {
+    int X, Y, Z;
+    int64_t sx, sy;        // element pitches of axis 0 and 1 (axis 2 pitch is 1)
+    T *buf[2][3];          // ping-pong state: step t reads buf[t&1], writes buf[(t+1)&1]
+    const T *coef[12];     // model dependent, see tgtk_api.cu
+    T cx, cy, cz;          // FK/FK_2c: Dw/h^2 ; DTI/COEF6/FACES: 1/h^2
+    T ex, ey, ez;          // FK_2c: Ds/h^2
+    T dt, rho;
+    T th_necro, lambda_np, sigma_np, lambda_s;
+    double vol_scale_p;    // dx*dy*dz
+    double vol_scale_n;    // FK_2c: 1.0 (sic, FK_2c.py:235); others unused
+    double stop_volume;
+    double small_volume;
+    Ctrl *ctrl;
+    double *partials;      // [2][nblocks] per-block sums (field 0, field 1)
+    double *volumes;       // per-step volume log
+    int volumes_cap;
+};
+
+// Arithmetic in the reference's rounding order: no FMA contraction (numpy evaluates every
+// ufunc separately), used where bit-exact agreement with the float64 reference is offered.
+template <typename T> struct Rn;
+template <> struct Rn<double> {
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+};
+template <> struct Rn<float> {
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+};
+
+__device__ __forceinline__ double tg_exp(double x) { return exp(x); }
+__device__ __forceinline__ float tg_exp(float x) { return expf(x); }
+__device__ __forceinline__ double tg_max(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float tg_max(float a, float b) { return fmaxf(a, b); }
+
+// smooth_heaviside, FK_2c/FK_2c.py:75-76 (k = 50)
+template <typename T> __device__ __forceinline__ T heaviside50(T s, T sigma)
+{
+    const T e = tg_exp(T(-50) * (s - sigma));
+    return T(1) - T(1) / (T(1) + e);
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum of up to two doubles per thread, then the deterministic last-block-done
+// final reduction, the volume / stop test of the reference loop and the step counter bump.
+// Every thread of every block of the launch must call this exactly once.
+template <typename T, int kFields>
+__device__ __forceinline__ void finish_step(const StepArgs<T> &a, int t, double s0, double s1)
+{
+    __shared__ double red[2][32];
+    __shared__ bool is_last;
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    const int nthreads = blockDim.x * blockDim.y * blockDim.z;
+    const int nwarps = (nthreads + 31) >> 5;
+    const int lane = tid & 31, warp = tid >> 5;
+    const unsigned nblocks = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+
+    s0 = warp_sum(s0);
+    if (kFields > 1) s1 = warp_sum(s1);
+    if (lane == 0) {
+        red[0][warp] = s0;
+        red[1][warp] = s1;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double v0 = (lane < nwarps) ? red[0][lane] : 0.0;
+        double v1 = (kFields > 1 && lane < nwarps) ? red[1][lane] : 0.0;
+        v0 = warp_sum(v0);
+        if (kFields > 1) v1 = warp_sum(v1);
+        if (lane == 0) {
+            a.partials[bid] = v0;
+            if (kFields > 1) a.partials[nblocks + bid] = v1;
+            __threadfence();
+            const unsigned done = atomicAdd(&a.ctrl->ticket, 1u);
+            is_last = (done == nblocks - 1);
+        }
+    }
+    __syncthreads();
+    if (!is_last) return;
+
+    // last block: fixed-order reduction of the per-block partials
+    __threadfence();
+    double v0 = 0.0, v1 = 0.0;
+    for (unsigned i = tid; i < nblocks; i += nthreads) {
+        v0 += __ldcg(&a.partials[i]);
+        if (kFields > 1) v1 += __ldcg(&a.partials[nblocks + i]);
+    }
+    v0 = warp_sum(v0);
+    if (kFields > 1) v1 = warp_sum(v1);
+    __syncthreads();
+    if (lane == 0) {
+        red[0][warp] = v0;
+        red[1][warp] = v1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double t0 = 0.0, t1 = 0.0;
+        for (int w = 0; w < nwarps; ++w) {
+            t0 += red[0][w];
+            t1 += red[1][w];
+        }
+        // FK/FK.py:215  volume = dx*dy*dz*sum(A);  FK_2c.py:235  dx*dy*dz*sum(P) + sum(N)
+        double vol = a.vol_scale_p * t0;
+        if (kFields > 1) vol += a.vol_scale_n * t1;
+        if (t < a.volumes_cap) a.volumes[t] = vol;
+        a.ctrl->last_volume = vol;
+        if (vol >= a.stop_volume) {
+            a.ctrl->stop_reason = 1;
+            a.ctrl->stop_step = t;
+        } else if (vol < a.small_volume) {
+            a.ctrl->stop_reason = 2;
+            a.ctrl->stop_step = t;
+        }
+        a.ctrl->t = t + 1;
+        a.ctrl->ticket = 0u;
+        __threadfence();
+    }
+}
+
+}  // namespace tgtk
