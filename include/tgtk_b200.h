@@ -109,6 +109,11 @@ int tgtk_device_count(int *count);
 int tgtk_sim_create(tgtk_sim **out, const tgtk_params *params, int device, void *stream);
 void tgtk_sim_destroy(tgtk_sim *sim);
 
+/* Kernel family: 2 (default) = tuned marching kernels, 1 = baseline one-voxel-per-thread
+ * kernels kept as the in-device cross-check.  The environment variable TGTK_VARIANT sets the
+ * default.  Both compute the same operator. */
+int tgtk_sim_set_variant(tgtk_sim *sim, int variant);
+
 /* Host -> device.  `host` is float64 with element strides (sx,sy,sz); any strides are
  * accepted (rows with sz==1 are copied directly, otherwise gathered on the host).  If
  * `pinned` is non-zero the caller promises page-locked memory and the copy is fully
@@ -120,6 +125,10 @@ int tgtk_sim_download(tgtk_sim *sim, int field, double *host, const int64_t stri
 /* Finish set-up once all inputs are uploaded: builds the per-voxel coefficient arrays
  * (get_D, FK/FK.py:22-32; get_D(…,D_s,1), FK_2c/FK_2c.py:216), resets the step counter. */
 int tgtk_sim_prepare(tgtk_sim *sim);
+
+/* Restore the state saved by tgtk_sim_prepare and restart the step counter at 0 (device to
+ * device; lets one uploaded problem be stepped repeatedly, e.g. by bench.py). */
+int tgtk_sim_reset(tgtk_sim *sim);
 
 /* Enqueue `nsteps` update steps (the body of the reference's `for t in range(...)` loops:
  * update, volume, stop test, snapshot).  `record_steps` (sorted, may be NULL) are absolute

@@ -20,11 +20,12 @@ def get_tensor_from_lower6(lower6):
 
 def elongate_tensor_along_main_axis_torch(tensor_arrayNP, scale_factor):
     """Scale the largest eigenvalue by `scale_factor`, shrink the other two so the trace is
-    kept, rebuild the tensors; float32 like the reference (tools.py:109-164).  Uses
-    torch.linalg.eigh on the GPU when one is present (8.9 M 3x3 problems at atlas size)."""
+    kept, rebuild the tensors; float32 torch.linalg.eigh on the CPU like the reference
+    (tools.py:109-164).  One-off preprocessing before the time loop; a batched 3x3 GPU eigh
+    is SURVEY.md 8(f) row F3 (cuSOLVER's syevBatched rejects this batch on sm_100)."""
     import torch
     with torch.no_grad():
-        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        dev = "cpu"
         t = torch.from_numpy(np.ascontiguousarray(tensor_arrayNP)).float().to(dev)
         e, v = torch.linalg.eigh(t)
         total = e.sum(dim=-1, keepdim=True)

@@ -70,6 +70,8 @@ def lib():
     L.tgtk_sim_upload.argtypes = [vp, ctypes.c_int, vp, _I64x3, ctypes.c_int]
     L.tgtk_sim_download.argtypes = [vp, ctypes.c_int, vp, _I64x3]
     L.tgtk_sim_prepare.argtypes = [vp]
+    L.tgtk_sim_set_variant.argtypes = [vp, ctypes.c_int]
+    L.tgtk_sim_reset.argtypes = [vp]
     L.tgtk_sim_run.argtypes = [vp, ctypes.c_int, ip, ctypes.c_int]
     L.tgtk_sim_sync.argtypes = [vp, ctypes.POINTER(Status)]
     L.tgtk_sim_volumes.argtypes = [vp, ctypes.c_int, ctypes.c_int, dp]
@@ -158,6 +160,12 @@ class Sim:
 
     def prepare(self):
         _check(lib().tgtk_sim_prepare(self._h))
+
+    def set_variant(self, variant):
+        _check(lib().tgtk_sim_set_variant(self._h, int(variant)))
+
+    def reset(self):
+        _check(lib().tgtk_sim_reset(self._h))
 
     def run(self, nsteps, record_steps=None):
         if record_steps is None or len(record_steps) == 0:

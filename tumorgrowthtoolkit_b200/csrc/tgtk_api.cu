@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -11,6 +12,7 @@
 #include "../../include/tgtk_b200.h"
 #include "tgtk_common.cuh"
 #include "tgtk_kernels_v1.cuh"
+#include "tgtk_kernels_v2.cuh"
 
 using namespace tgtk;
 
@@ -40,6 +42,7 @@ struct tgtk_sim {
     void *state[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     void *coef[12] = {nullptr};
     double *stage = nullptr;  // dense float64 staging for uploads / downloads
+    void *initial[3] = {nullptr, nullptr, nullptr};  // state at prepare time (tgtk_sim_reset)
     double *wm = nullptr, *gm = nullptr, *pc = nullptr, *pn = nullptr;
     int faces_what = 0;  // tgtk_faces_host: 0 D_minus, 1 WM_tilda, 2 GM_tilda
     Ctrl *ctrl = nullptr;
@@ -51,7 +54,9 @@ struct tgtk_sim {
     unsigned nblocks = 0;
     int t_enqueued = 0;
     bool prepared = false;
-    int kernel_variant = 0;
+    int variant = 2;       // 1: baseline kernels, 2: marching kernels (tgtk_kernels_v2.cuh)
+    int lx = 1;            // planes per block of the marching kernels
+    unsigned partials_cap = 0;
     std::vector<void *> snaps;     // one allocation per snapshot: nfields * n * elem
     std::vector<int> snap_steps;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -180,6 +185,14 @@ template <typename T> static cudaError_t launch_step(tgtk_sim *s)
 {
     StepArgs<T> a;
     fill_args(s, a);
+    if (s->lx > 0) {   // marching geometry chosen by configure_launch
+        switch (s->p.model) {
+        case TGTK_MODEL_FK: fk_step_v2<T><<<s->grid, s->block, 0, s->stream>>>(a, s->lx); return cudaGetLastError();
+        case TGTK_MODEL_FK_2C: fk2c_step_v2<T><<<s->grid, s->block, 0, s->stream>>>(a, s->lx); return cudaGetLastError();
+        case TGTK_MODEL_DTI: dti_step_v2<T><<<s->grid, s->block, 0, s->stream>>>(a, s->lx); return cudaGetLastError();
+        default: break;
+        }
+    }
     switch (s->p.model) {
     case TGTK_MODEL_FK: fk_step_v1<T><<<s->grid, s->block, 0, s->stream>>>(a); break;
     case TGTK_MODEL_FK_2C: fk2c_step_v1<T><<<s->grid, s->block, 0, s->stream>>>(a); break;
@@ -190,6 +203,47 @@ template <typename T> static cudaError_t launch_step(tgtk_sim *s)
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
+}
+
+static bool has_v2(int model) { return model == TGTK_MODEL_FK || model == TGTK_MODEL_FK_2C || model == TGTK_MODEL_DTI; }
+
+// Launch geometry.  Baseline: 32x4x2 voxels per block.  Marching: a (TZ x TY) column tile per
+// block, TZ in {64,32,16} picked to waste the fewest lanes on the ragged z edge, and the x
+// axis cut into segments so that the grid is a few waves of the 148 SMs.
+static int configure_launch(tgtk_sim *s)
+{
+    const tgtk_params &p = s->p;
+    const bool fits32 = (uint64_t)p.X * (uint64_t)s->sx < (1ull << 31);   // 32-bit element offsets
+    if (s->variant == 2 && has_v2(p.model) && fits32) {
+        int best_tz = 32;
+        double best = 1e30;
+        for (int tz : {64, 32, 16}) {
+            const int ty = 256 / tz;
+            const double padded = (double)((p.Z + tz - 1) / tz * tz) * ((p.Y + ty - 1) / ty * ty);
+            const double cost = padded / ((double)p.Z * p.Y) + 0.02 * (tz == 16) + 0.03 * (tz == 64);
+            if (cost < best) { best = cost; best_tz = tz; }
+        }
+        const int tz = best_tz, ty = 256 / tz;
+        const int tiles = ((p.Z + tz - 1) / tz) * ((p.Y + ty - 1) / ty);
+        const int target_blocks = 148 * 2 * 4;
+        int nseg = std::max(1, std::min(p.X, (target_blocks + tiles - 1) / tiles));
+        s->lx = (p.X + nseg - 1) / nseg;
+        nseg = (p.X + s->lx - 1) / s->lx;
+        s->block = dim3(tz, ty, 1);
+        s->grid = dim3((p.Z + tz - 1) / tz, (p.Y + ty - 1) / ty, nseg);
+    } else {
+        s->lx = 0;
+        s->block = dim3(32, 4, 2);
+        s->grid = dim3((p.Z + 31) / 32, (p.Y + 3) / 4, (p.X + 1) / 2);
+    }
+    s->nblocks = s->grid.x * s->grid.y * s->grid.z;
+    if (s->nblocks > s->partials_cap) {
+        if (s->partials) CU(cudaFree(s->partials));
+        s->partials = nullptr;
+        CU(cudaMalloc(&s->partials, sizeof(double) * 2 * s->nblocks));
+        s->partials_cap = s->nblocks;
+    }
+    return 0;
 }
 
 static int ensure_volumes(tgtk_sim *s, int need)
@@ -309,10 +363,9 @@ int tgtk_sim_create(tgtk_sim **out, const tgtk_params *params, int device, void 
     case TGTK_MODEL_FK_FACES: s->ncoef = 3; break;
     case TGTK_MODEL_FK2C_COEF12: s->ncoef = 12; break;
     }
-    s->block = dim3(32, 4, 2);
-    s->grid = dim3((p.Z + 31) / 32, (p.Y + 3) / 4, (p.X + 1) / 2);
-    s->nblocks = s->grid.x * s->grid.y * s->grid.z;
+    if (const char *v = getenv("TGTK_VARIANT")) s->variant = atoi(v);
     *out = s;  // from here on tgtk_sim_destroy cleans up on failure
+    if (configure_launch(s)) return 1;
     const size_t bytes = (size_t)p.X * s->sx * s->elem;
     for (int b = 0; b < 2; ++b)
         for (int f = 0; f < s->nfields; ++f) {
@@ -326,7 +379,6 @@ int tgtk_sim_create(tgtk_sim **out, const tgtk_params *params, int device, void 
     CU(cudaMalloc(&s->stage, s->n * 8));
     CU(cudaMalloc(&s->ctrl, sizeof(Ctrl)));
     CU(cudaMallocHost(&s->ctrl_host, sizeof(Ctrl)));
-    CU(cudaMalloc(&s->partials, sizeof(double) * 2 * s->nblocks));
     CU(cudaEventCreate(&s->ev0));
     CU(cudaEventCreate(&s->ev1));
     Ctrl init = {0, 0, -1, 0u, 0.0};
@@ -347,6 +399,7 @@ void tgtk_sim_destroy(tgtk_sim *s)
     for (int c = 0; c < 12; ++c) cudaFree(s->coef[c]);
     for (void *q : s->snaps) cudaFree(q);
     cudaFree(s->stage);
+    for (int f = 0; f < 3; ++f) cudaFree(s->initial[f]);
     cudaFree(s->wm);
     cudaFree(s->gm);
     cudaFree(s->pc);
@@ -359,6 +412,16 @@ void tgtk_sim_destroy(tgtk_sim *s)
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     delete s;
+}
+
+int tgtk_sim_set_variant(tgtk_sim *s, int variant)
+{
+    if (!s) return fail("tgtk_sim_set_variant", "null argument");
+    if (variant != 1 && variant != 2) return fail("tgtk_sim_set_variant", "variant must be 1 or 2");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    s->variant = variant;
+    return configure_launch(s);
 }
 
 int tgtk_sim_upload(tgtk_sim *s, int field, const double *host, const int64_t strides[3], int pinned)
@@ -467,7 +530,33 @@ int tgtk_sim_prepare(tgtk_sim *s)
         CU(cudaFree(s->pn));
         s->wm = s->gm = s->pc = s->pn = nullptr;
     }
+    // keep the initial state so a finished loop can be rerun without another upload
+    const size_t bytes = (size_t)p.X * s->sx * s->elem;
+    const int cur = s->t_enqueued & 1;
+    for (int f = 0; f < s->nfields; ++f) {
+        if (!s->initial[f]) CU(cudaMalloc(&s->initial[f], bytes));
+        CU(cudaMemcpyAsync(s->initial[f], s->state[cur][f], bytes, cudaMemcpyDeviceToDevice, s->stream));
+    }
     s->prepared = true;
+    return 0;
+}
+
+int tgtk_sim_reset(tgtk_sim *s)
+{
+    if (!s) return fail("tgtk_sim_reset", "null argument");
+    if (!s->prepared) return fail("tgtk_sim_reset", "call tgtk_sim_prepare first");
+    CU(cudaSetDevice(s->device));
+    const size_t bytes = (size_t)s->p.X * s->sx * s->elem;
+    for (int f = 0; f < s->nfields; ++f)
+        CU(cudaMemcpyAsync(s->state[0][f], s->initial[f], bytes, cudaMemcpyDeviceToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));   // ctrl_host is about to be rewritten
+    Ctrl init = {0, 0, -1, 0u, 0.0};
+    *s->ctrl_host = init;
+    CU(cudaMemcpyAsync(s->ctrl, s->ctrl_host, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
+    for (void *q : s->snaps) cudaFree(q);
+    s->snaps.clear();
+    s->snap_steps.clear();
+    s->t_enqueued = 0;
     return 0;
 }
 

@@ -61,6 +61,16 @@ __device__ __forceinline__ float tg_exp(float x) { return expf(x); }
 __device__ __forceinline__ double tg_max(double a, double b) { return fmax(a, b); }
 __device__ __forceinline__ float tg_max(float a, float b) { return fmaxf(a, b); }
 
+// max(x, 0) for finite x.  fp64 fmax() compiles to 7 SASS instructions (DSETP.MAX plus NaN
+// fix-up) and sits on the fp64 pipe; masking with the sign bit is 3 integer ops.
+__device__ __forceinline__ double relu(double x)
+{
+    const int hi = __double2hiint(x);
+    const int keep = ~(hi >> 31);
+    return __hiloint2double(hi & keep, __double2loint(x) & keep);
+}
+__device__ __forceinline__ float relu(float x) { return fmaxf(x, 0.0f); }
+
 // smooth_heaviside, FK_2c/FK_2c.py:75-76 (k = 50)
 template <typename T> __device__ __forceinline__ T heaviside50(T s, T sigma)
 {
