@@ -13,8 +13,12 @@
 #include "tgtk_common.cuh"
 #include "tgtk_kernels_v1.cuh"
 #include "tgtk_kernels_v2.cuh"
+#include "tgtk_kernels_v3.cuh"
 
 using namespace tgtk;
+
+// steps per CUDA-graph replay = slots of the partial-sum ring of the host-scheduled mode
+static const int kGraphSteps = 32;
 
 static thread_local std::string g_err;
 
@@ -54,8 +58,14 @@ struct tgtk_sim {
     unsigned nblocks = 0;
     int t_enqueued = 0;
     bool prepared = false;
-    int variant = 2;       // 1: baseline kernels, 2: marching kernels (tgtk_kernels_v2.cuh)
+    int variant = 3;       // 1: baseline, 2: marching via L1, 3: marching via shared memory (default)
     int lx = 1;            // planes per block of the marching kernels
+    int force_tz = 0;      // 0: pick the tile width by lane waste
+    bool use_graph = true;
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // by parity of the first step
+    bool host_sched = false;   // no stop criterion: parity baked into launches (see StepArgs)
+    int cur_par = 0, cur_slot = 0;   // launch-time values of StepArgs::par / slot
+    int minb = 3;          // FK_2c staged kernel: resident blocks per SM the register budget targets
     unsigned partials_cap = 0;
     std::vector<void *> snaps;     // one allocation per snapshot: nfields * n * elem
     std::vector<int> snap_steps;
@@ -179,12 +189,41 @@ template <typename T> static void fill_args(const tgtk_sim *s, StepArgs<T> &a)
     a.partials = s->partials;
     a.volumes = s->volumes;
     a.volumes_cap = s->volumes_cap;
+    a.host_sched = s->host_sched ? 1 : 0;
+    a.par = s->cur_par;
+    a.slot = s->cur_slot;
 }
 
 template <typename T> static cudaError_t launch_step(tgtk_sim *s)
 {
     StepArgs<T> a;
     fill_args(s, a);
+    if (s->lx > 0 && s->variant == 3) {   // shared-memory staged marching kernels
+        const bool wide = (s->block.x == 32);
+        switch (s->p.model) {
+        case TGTK_MODEL_FK:
+            if (wide) fk_step_v3<T, 32, 8><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+            else fk_step_v3<T, 16, 16><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+            return cudaGetLastError();
+        case TGTK_MODEL_FK_2C:
+            if (s->minb == 4) {
+                if (wide) fk2c_step_v3<T, 32, 8, 4><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+                else fk2c_step_v3<T, 16, 16, 4><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+            } else if (s->minb == 3) {
+                if (wide) fk2c_step_v3<T, 32, 8, 3><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+                else fk2c_step_v3<T, 16, 16, 3><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+            } else {
+                if (wide) fk2c_step_v3<T, 32, 8><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+                else fk2c_step_v3<T, 16, 16><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+            }
+            return cudaGetLastError();
+        case TGTK_MODEL_DTI:
+            if (wide) dti_step_v3<T, 32, 8><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+            else dti_step_v3<T, 16, 16><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+            return cudaGetLastError();
+        default: break;
+        }
+    }
     if (s->lx > 0) {   // marching geometry chosen by configure_launch
         switch (s->p.model) {
         case TGTK_MODEL_FK: fk_step_v2<T><<<s->grid, s->block, 0, s->stream>>>(a, s->lx); return cudaGetLastError();
@@ -205,6 +244,35 @@ template <typename T> static cudaError_t launch_step(tgtk_sim *s)
     return cudaGetLastError();
 }
 
+template <typename T> static const void *v2_kernel(int model)
+{
+    switch (model) {
+    case TGTK_MODEL_FK: return (const void *)fk_step_v2<T>;
+    case TGTK_MODEL_FK_2C: return (const void *)fk2c_step_v2<T>;
+    default: return (const void *)dti_step_v2<T>;
+    }
+}
+
+template <typename T> static const void *v3_kernel(int model, bool wide, int minb)
+{
+    switch (model) {
+    case TGTK_MODEL_FK: return wide ? (const void *)fk_step_v3<T, 32, 8> : (const void *)fk_step_v3<T, 16, 16>;
+    case TGTK_MODEL_FK_2C:
+        if (minb == 4) return wide ? (const void *)fk2c_step_v3<T, 32, 8, 4> : (const void *)fk2c_step_v3<T, 16, 16, 4>;
+        if (minb == 3) return wide ? (const void *)fk2c_step_v3<T, 32, 8, 3> : (const void *)fk2c_step_v3<T, 16, 16, 3>;
+        return wide ? (const void *)fk2c_step_v3<T, 32, 8> : (const void *)fk2c_step_v3<T, 16, 16>;
+    default: return wide ? (const void *)dti_step_v3<T, 32, 8> : (const void *)dti_step_v3<T, 16, 16>;
+    }
+}
+
+static void drop_graph(tgtk_sim *s)
+{
+    for (int i = 0; i < 2; ++i) {
+        if (s->graph_exec[i]) cudaGraphExecDestroy(s->graph_exec[i]);
+        s->graph_exec[i] = nullptr;
+    }
+}
+
 static bool has_v2(int model) { return model == TGTK_MODEL_FK || model == TGTK_MODEL_FK_2C || model == TGTK_MODEL_DTI; }
 
 // Launch geometry.  Baseline: 32x4x2 voxels per block.  Marching: a (TZ x TY) column tile per
@@ -214,10 +282,12 @@ static int configure_launch(tgtk_sim *s)
 {
     const tgtk_params &p = s->p;
     const bool fits32 = (uint64_t)p.X * (uint64_t)s->sx < (1ull << 31);   // 32-bit element offsets
-    if (s->variant == 2 && has_v2(p.model) && fits32) {
+    if (s->variant >= 2 && has_v2(p.model) && fits32) {
         int best_tz = 32;
         double best = 1e30;
         for (int tz : {64, 32, 16}) {
+            if (s->variant == 3 && tz == 64) continue;   // staged kernels: 32x8 or 16x16 tiles
+            if (s->force_tz && tz != s->force_tz) continue;
             const int ty = 256 / tz;
             const double padded = (double)((p.Z + tz - 1) / tz * tz) * ((p.Y + ty - 1) / ty * ty);
             const double cost = padded / ((double)p.Z * p.Y) + 0.02 * (tz == 16) + 0.03 * (tz == 64);
@@ -225,10 +295,25 @@ static int configure_launch(tgtk_sim *s)
         }
         const int tz = best_tz, ty = 256 / tz;
         const int tiles = ((p.Z + tz - 1) / tz) * ((p.Y + ty - 1) / ty);
-        const int target_blocks = 148 * 2 * 4;
-        int nseg = std::max(1, std::min(p.X, (target_blocks + tiles - 1) / tiles));
-        s->lx = (p.X + nseg - 1) / nseg;
-        nseg = (p.X + s->lx - 1) / s->lx;
+        // Segment length: trade the tail of the last wave (blocks / resident slots not an
+        // integer) against the two extra planes every segment loads to prime its pipeline.
+        int per_sm = 2, sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+        const void *fn = (s->variant == 3)
+                             ? ((p.dtype == TGTK_F64) ? v3_kernel<double>(p.model, tz == 32, s->minb) : v3_kernel<float>(p.model, tz == 32, s->minb))
+                             : ((p.dtype == TGTK_F64) ? v2_kernel<double>(p.model) : v2_kernel<float>(p.model));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+        const double slots = (double)sms * per_sm;
+        int best_lx = p.X;
+        double best_eff = -1.0;
+        for (int lx = 1; lx <= p.X; ++lx) {
+            const int ns = (p.X + lx - 1) / lx;
+            const double waves = tiles * (double)ns / slots;
+            const double eff = waves / std::ceil(waves) * (lx / (lx + 0.6)) * ((double)p.X / ((double)ns * lx));
+            if (eff > best_eff + 1e-9) { best_eff = eff; best_lx = lx; }
+        }
+        s->lx = best_lx;
+        const int nseg = (p.X + s->lx - 1) / s->lx;
         s->block = dim3(tz, ty, 1);
         s->grid = dim3((p.Z + tz - 1) / tz, (p.Y + ty - 1) / ty, nseg);
     } else {
@@ -237,10 +322,11 @@ static int configure_launch(tgtk_sim *s)
         s->grid = dim3((p.Z + 31) / 32, (p.Y + 3) / 4, (p.X + 1) / 2);
     }
     s->nblocks = s->grid.x * s->grid.y * s->grid.z;
+    drop_graph(s);
     if (s->nblocks > s->partials_cap) {
         if (s->partials) CU(cudaFree(s->partials));
         s->partials = nullptr;
-        CU(cudaMalloc(&s->partials, sizeof(double) * 2 * s->nblocks));
+        CU(cudaMalloc(&s->partials, sizeof(double) * 2 * s->nblocks * kGraphSteps));   // ring of kGraphSteps slots
         s->partials_cap = s->nblocks;
     }
     return 0;
@@ -260,6 +346,42 @@ static int ensure_volumes(tgtk_sim *s, int need)
     }
     s->volumes = nv;
     s->volumes_cap = cap;
+    drop_graph(s);   // the log pointer is a kernel argument
+    return 0;
+}
+
+// kGraphSteps consecutive step launches captured once and replayed: every launch has the same
+// arguments because the step index and the ping-pong parity are read from Ctrl on the device.
+
+static cudaError_t launch_one(tgtk_sim *s, int par, int slot)
+{
+    s->cur_par = par;
+    s->cur_slot = slot;
+    return (s->p.dtype == TGTK_F64) ? launch_step<double>(s) : launch_step<float>(s);
+}
+
+static cudaError_t launch_chunk_finish(tgtk_sim *s, int count)
+{
+    const tgtk_params &p = s->p;
+    chunk_finish_kernel<<<1, 1024, 0, s->stream>>>(s->ctrl, s->partials, s->volumes, s->volumes_cap, s->nblocks, s->nfields,
+                                                   count, p.h[0] * p.h[1] * p.h[2], 1.0);
+    return cudaGetLastError();
+}
+
+// One graph per parity of its first step: in host-scheduled mode the parity is a launch argument.
+static int build_graph(tgtk_sim *s, int par0)
+{
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < kGraphSteps && e == cudaSuccess; ++i) e = launch_one(s, (par0 + i) & 1, i);
+    if (e == cudaSuccess && s->host_sched) e = launch_chunk_finish(s, kGraphSteps);
+    cudaError_t e2 = cudaStreamEndCapture(s->stream, &graph);
+    if (e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail("graph capture", cudaGetErrorString(e)); }
+    if (e2 != cudaSuccess) return fail("cudaStreamEndCapture", cudaGetErrorString(e2));
+    e = cudaGraphInstantiate(&s->graph_exec[par0], graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { s->graph_exec[par0] = nullptr; return fail("cudaGraphInstantiate", cudaGetErrorString(e)); }
     return 0;
 }
 
@@ -364,6 +486,9 @@ int tgtk_sim_create(tgtk_sim **out, const tgtk_params *params, int device, void 
     case TGTK_MODEL_FK2C_COEF12: s->ncoef = 12; break;
     }
     if (const char *v = getenv("TGTK_VARIANT")) s->variant = atoi(v);
+    if (const char *v = getenv("TGTK_MINB")) s->minb = atoi(v);
+    if (const char *v = getenv("TGTK_GRAPH")) s->use_graph = atoi(v) != 0;
+    if (const char *v = getenv("TGTK_TZ")) s->force_tz = atoi(v);
     *out = s;  // from here on tgtk_sim_destroy cleans up on failure
     if (configure_launch(s)) return 1;
     const size_t bytes = (size_t)p.X * s->sx * s->elem;
@@ -408,6 +533,7 @@ void tgtk_sim_destroy(tgtk_sim *s)
     cudaFree(s->partials);
     cudaFree(s->volumes);
     if (s->ctrl_host) cudaFreeHost(s->ctrl_host);
+    drop_graph(s);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
@@ -417,7 +543,7 @@ void tgtk_sim_destroy(tgtk_sim *s)
 int tgtk_sim_set_variant(tgtk_sim *s, int variant)
 {
     if (!s) return fail("tgtk_sim_set_variant", "null argument");
-    if (variant != 1 && variant != 2) return fail("tgtk_sim_set_variant", "variant must be 1 or 2");
+    if (variant < 1 || variant > 3) return fail("tgtk_sim_set_variant", "variant must be 1, 2 or 3");
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(s->stream));
     s->variant = variant;
@@ -530,6 +656,14 @@ int tgtk_sim_prepare(tgtk_sim *s)
         CU(cudaFree(s->pn));
         s->wm = s->gm = s->pc = s->pn = nullptr;
     }
+    // no stop criterion active -> host-scheduled launches (see StepArgs::host_sched)
+    {
+        const bool want = std::isinf(p.stopping_volume) && p.stopping_volume > 0 && !(p.small_volume > 0);
+        const char *v = getenv("TGTK_HOST_SCHED");
+        const bool host_sched = want && !(v && atoi(v) == 0);
+        if (host_sched != s->host_sched) drop_graph(s);
+        s->host_sched = host_sched;
+    }
     // keep the initial state so a finished loop can be rerun without another upload
     const size_t bytes = (size_t)p.X * s->sx * s->elem;
     const int cur = s->t_enqueued & 1;
@@ -570,26 +704,53 @@ int tgtk_sim_run(tgtk_sim *s, int nsteps, const int32_t *record_steps, int nreco
     const size_t bytes = (size_t)s->p.X * s->sx * s->elem;
     int r = 0;
     while (r < nrecord && record_steps[r] < s->t_enqueued) ++r;
+    // snapshot arenas are allocated up front: cudaMalloc inside the loop would serialise it
+    int nsnap = 0;
+    for (int i = r; i < nrecord; ++i)
+        if (record_steps[i] < s->t_enqueued + nsteps && (i == r || record_steps[i] != record_steps[i - 1])) ++nsnap;
+    std::vector<void *> arenas(nsnap, nullptr);
+    for (int i = 0; i < nsnap; ++i) CU(cudaMalloc(&arenas[i], bytes * s->nfields));
+    int used = 0;
     CU(cudaEventRecord(s->ev0, s->stream));
-    for (int q = 0; q < nsteps; ++q) {
-        const int t = s->t_enqueued;
-        cudaError_t e = (s->p.dtype == TGTK_F64) ? launch_step<double>(s) : launch_step<float>(s);
-        if (e != cudaSuccess) return fail("step launch", cudaGetErrorString(e));
-        ++s->launches;
-        ++s->t_enqueued;
-        bool rec = false;
-        while (r < nrecord && record_steps[r] == t) { rec = true; ++r; }
-        if (rec) {
+    int q = 0;
+    while (q < nsteps) {
+        // steps up to and including the next record step (or the end of this run)
+        const int t0 = s->t_enqueued;
+        const int next_rec = (r < nrecord) ? record_steps[r] : 0x7fffffff;
+        const int run_len = (int)std::min<int64_t>(nsteps - q, (int64_t)next_rec - t0 + 1);
+        int done = 0;
+        // identical launches (the step index lives in device memory) replayed from a CUDA graph
+        while (s->use_graph && run_len - done >= kGraphSteps) {
+            const int par0 = (t0 + done) & 1;
+            if (!s->graph_exec[par0] && build_graph(s, par0)) return 1;
+            CU(cudaGraphLaunch(s->graph_exec[par0], s->stream));
+            done += kGraphSteps;
+        }
+        while (done < run_len) {
+            // leftovers: plain launches, in host-scheduled mode closed by one chunk_finish
+            const int n = std::min(run_len - done, kGraphSteps);
+            cudaError_t e = cudaSuccess;
+            for (int i = 0; i < n && e == cudaSuccess; ++i) e = launch_one(s, (t0 + done + i) & 1, i);
+            if (e == cudaSuccess && s->host_sched) e = launch_chunk_finish(s, n);
+            if (e != cudaSuccess) return fail("step launch", cudaGetErrorString(e));
+            done += n;
+        }
+        s->launches += run_len;
+        s->t_enqueued += run_len;
+        q += run_len;
+        const int t = s->t_enqueued - 1;
+        if (t == next_rec) {
             // state after step t lives in buf[(t+1)&1]; FK/FK.py:221-223
-            void *arena = nullptr;
-            CU(cudaMalloc(&arena, bytes * s->nfields));
+            void *arena = arenas[used++];
             for (int f = 0; f < s->nfields; ++f)
                 CU(cudaMemcpyAsync((char *)arena + bytes * f, s->state[(t + 1) & 1][f], bytes, cudaMemcpyDeviceToDevice,
                                    s->stream));
             s->snaps.push_back(arena);
             s->snap_steps.push_back(t);
+            while (r < nrecord && record_steps[r] == t) ++r;
         }
     }
+    for (int i = used; i < nsnap; ++i) cudaFree(arenas[i]);
     CU(cudaEventRecord(s->ev1, s->stream));
     s->timed = true;
     return 0;

@@ -40,7 +40,33 @@ template <typename T> struct StepArgs {
     double *partials;      // [2][nblocks] per-block sums (field 0, field 1)
     double *volumes;       // per-step volume log
     int volumes_cap;
+    // Scheduling.  host_sched = 0: the step index and the stop flag live on the device (Ctrl)
+    // and are read at kernel start; the last block to finish reduces the volume and runs the
+    // reference's stop tests.  host_sched = 1 (no stop criterion active): the ping-pong parity
+    // is baked into the launch, blocks only deposit their partial sums in ring slot `slot`, and
+    // chunk_finish_kernel reduces a whole chunk of steps later -- nothing on the step-to-step
+    // critical path depends on a device-side read-modify-write.
+    int host_sched, par, slot;
 };
+
+struct StepCtl {
+    int t;       // step index (device-scheduled mode), -1 otherwise
+    int par;     // index of the buffer holding the current state
+    bool stop;
+};
+
+template <typename T> __device__ __forceinline__ StepCtl step_begin(const StepArgs<T> &a)
+{
+    StepCtl c;
+    if (a.host_sched) {
+        c.t = -1; c.par = a.par; c.stop = false;
+    } else {
+        c.t = a.ctrl->t;
+        c.par = c.t & 1;
+        c.stop = (a.ctrl->stop_reason != 0);
+    }
+    return c;
+}
 
 // Arithmetic in the reference's rounding order: no FMA contraction (numpy evaluates every
 // ufunc separately), used where bit-exact agreement with the float64 reference is offered.
@@ -160,6 +186,77 @@ __device__ __forceinline__ void finish_step(const StepArgs<T> &a, int t, double 
         a.ctrl->ticket = 0u;
         __threadfence();
     }
+}
+
+// host-scheduled mode: per-block partial sums into ring slot a.slot, nothing else
+template <typename T, int kFields>
+__device__ __forceinline__ void finish_light(const StepArgs<T> &a, double s0, double s1)
+{
+    __shared__ double red2[2][32];
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    const int nthreads = blockDim.x * blockDim.y * blockDim.z;
+    const int nwarps = (nthreads + 31) >> 5;
+    const int lane = tid & 31, warp = tid >> 5;
+    const unsigned nblocks = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    s0 = warp_sum(s0);
+    if (kFields > 1) s1 = warp_sum(s1);
+    if (lane == 0) {
+        red2[0][warp] = s0;
+        red2[1][warp] = s1;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double v0 = (lane < nwarps) ? red2[0][lane] : 0.0;
+        double v1 = (kFields > 1 && lane < nwarps) ? red2[1][lane] : 0.0;
+        v0 = warp_sum(v0);
+        if (kFields > 1) v1 = warp_sum(v1);
+        if (lane == 0) {
+            double *ring = a.partials + (size_t)a.slot * 2 * nblocks;
+            ring[bid] = v0;
+            if (kFields > 1) ring[nblocks + bid] = v1;
+        }
+    }
+}
+
+template <typename T, int kFields>
+__device__ __forceinline__ void step_end(const StepArgs<T> &a, const StepCtl &c, double s0, double s1)
+{
+    if (a.host_sched) finish_light<T, kFields>(a, s0, s1);
+    else finish_step<T, kFields>(a, c.t, s0, s1);
+}
+
+// Reduces the partial sums of `count` consecutive host-scheduled steps (ring slots 0..count-1)
+// in a fixed order, logs the volumes and advances the device step counter.  One block.
+__global__ void __launch_bounds__(1024) chunk_finish_kernel(Ctrl *ctrl, const double *partials, double *volumes,
+                                                            int volumes_cap, unsigned nblocks, int nfields, int count,
+                                                            double scale_p, double scale_n)
+{
+    __shared__ double red[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t0 = ctrl->t;
+    for (int j = 0; j < count; ++j) {
+        const double *ring = partials + (size_t)j * 2 * nblocks;
+        double v0 = 0.0, v1 = 0.0;
+        for (unsigned i = tid; i < nblocks; i += 1024) {
+            v0 += ring[i];
+            if (nfields > 1) v1 += ring[nblocks + i];
+        }
+        v0 = warp_sum(v0);
+        v1 = warp_sum(v1);
+        __syncthreads();
+        if (lane == 0) { red[0][warp] = v0; red[1][warp] = v1; }
+        __syncthreads();
+        if (tid == 0) {
+            double a0 = 0.0, a1 = 0.0;
+            for (int w = 0; w < 32; ++w) { a0 += red[0][w]; a1 += red[1][w]; }
+            double vol = scale_p * a0;
+            if (nfields > 1) vol += scale_n * a1;
+            if (t0 + j < volumes_cap) volumes[t0 + j] = vol;
+            if (j == count - 1) ctrl->last_volume = vol;
+        }
+    }
+    if (tid == 0) ctrl->t = t0 + count;
 }
 
 }  // namespace tgtk

@@ -37,10 +37,10 @@ __device__ __forceinline__ bool voxel_index(const StepArgs<T> &a, int &i, int &j
 // coefficient of FK/FK.py:10-26 is Dw*max(k(c)+k(c'),0); Dw/h^2 is folded into cx,cy,cz.
 template <typename T> __global__ void __launch_bounds__(256) fk_step_v1(const StepArgs<T> a)
 {
-    const int t = a.ctrl->t;
-    if (a.ctrl->stop_reason != 0) return;
-    const T *__restrict__ u = a.buf[t & 1][0];
-    T *__restrict__ o = a.buf[(t + 1) & 1][0];
+    const StepCtl sc = step_begin(a);
+    if (sc.stop) return;
+    const T *__restrict__ u = a.buf[sc.par][0];
+    T *__restrict__ o = a.buf[sc.par ^ 1][0];
     const T *__restrict__ kc = a.coef[0];
     int i, j, k;
     Nbr n;
@@ -57,7 +57,7 @@ template <typename T> __global__ void __launch_bounds__(256) fk_step_v1(const St
         o[n.c] = un;
         s = (double)un;
     }
-    finish_step<T, 1>(a, t, s, 0.0);
+    step_end<T, 1>(a, sc, s, 0.0);
 }
 
 // ---- explicit coefficient arrays, reference rounding order --------------------------------
@@ -67,10 +67,10 @@ template <typename T> __global__ void __launch_bounds__(256) fk_step_v1(const St
 template <typename T, int kMode> __global__ void __launch_bounds__(256) coef_step_v1(const StepArgs<T> a)
 {
     using R = Rn<T>;
-    const int t = a.ctrl->t;
-    if (a.ctrl->stop_reason != 0) return;
-    const T *__restrict__ u = a.buf[t & 1][0];
-    T *__restrict__ o = a.buf[(t + 1) & 1][0];
+    const StepCtl sc = step_begin(a);
+    if (sc.stop) return;
+    const T *__restrict__ u = a.buf[sc.par][0];
+    T *__restrict__ o = a.buf[sc.par ^ 1][0];
     int i, j, k;
     Nbr n;
     double s = 0.0;
@@ -96,7 +96,7 @@ template <typename T, int kMode> __global__ void __launch_bounds__(256) coef_ste
         o[n.c] = un;
         s = (double)un;
     }
-    finish_step<T, 1>(a, t, s, 0.0);
+    step_end<T, 1>(a, sc, s, 0.0);
 }
 
 // ---- FK_2c, compact coefficients ----------------------------------------------------------
@@ -107,14 +107,14 @@ template <typename T, int kMode> __global__ void __launch_bounds__(256) coef_ste
 // N and the S sink use the new P.
 template <typename T> __global__ void __launch_bounds__(256) fk2c_step_v1(const StepArgs<T> a)
 {
-    const int t = a.ctrl->t;
-    if (a.ctrl->stop_reason != 0) return;
-    const T *__restrict__ P = a.buf[t & 1][0];
-    const T *__restrict__ N = a.buf[t & 1][1];
-    const T *__restrict__ S = a.buf[t & 1][2];
-    T *__restrict__ Po = a.buf[(t + 1) & 1][0];
-    T *__restrict__ No = a.buf[(t + 1) & 1][1];
-    T *__restrict__ So = a.buf[(t + 1) & 1][2];
+    const StepCtl sc = step_begin(a);
+    if (sc.stop) return;
+    const T *__restrict__ P = a.buf[sc.par][0];
+    const T *__restrict__ N = a.buf[sc.par][1];
+    const T *__restrict__ S = a.buf[sc.par][2];
+    T *__restrict__ Po = a.buf[sc.par ^ 1][0];
+    T *__restrict__ No = a.buf[sc.par ^ 1][1];
+    T *__restrict__ So = a.buf[sc.par ^ 1][2];
     const T *__restrict__ kc = a.coef[0];
     const T *__restrict__ bc = a.coef[1];
     int i, j, k;
@@ -143,7 +143,7 @@ template <typename T> __global__ void __launch_bounds__(256) fk2c_step_v1(const 
         sP = (double)pn;
         sN = (double)nnew;
     }
-    finish_step<T, 2>(a, t, sP, sN);
+    step_end<T, 2>(a, sc, sP, sN);
 }
 
 // ---- FK_2c with twelve explicit coefficient arrays, reference rounding order ---------------
@@ -152,11 +152,11 @@ template <typename T> __global__ void __launch_bounds__(256) fk2c_step_v1(const 
 template <typename T> __global__ void __launch_bounds__(256) fk2c_coef_step_v1(const StepArgs<T> a)
 {
     using R = Rn<T>;
-    const int t = a.ctrl->t;
-    if (a.ctrl->stop_reason != 0) return;
-    const T *__restrict__ P = a.buf[t & 1][0];
-    const T *__restrict__ N = a.buf[t & 1][1];
-    const T *__restrict__ S = a.buf[t & 1][2];
+    const StepCtl sc = step_begin(a);
+    if (sc.stop) return;
+    const T *__restrict__ P = a.buf[sc.par][0];
+    const T *__restrict__ N = a.buf[sc.par][1];
+    const T *__restrict__ S = a.buf[sc.par][2];
     int i, j, k;
     Nbr n;
     double sP = 0.0, sN = 0.0;
@@ -177,13 +177,13 @@ template <typename T> __global__ void __launch_bounds__(256) fk2c_coef_step_v1(c
                                    term(a.cy, a.coef[7][n.c], a.coef[10][n.c], S[n.ym], s, S[n.yp])),
                             term(a.cz, a.coef[8][n.c], a.coef[11][n.c], S[n.zm], s, S[n.zp]));
         const T snew = R::add(s, R::mul(R::sub(ss, R::mul(R::mul(a.lambda_s, s), pn)), a.dt));
-        a.buf[(t + 1) & 1][0][n.c] = pn;
-        a.buf[(t + 1) & 1][1][n.c] = nnew;
-        a.buf[(t + 1) & 1][2][n.c] = snew;
+        a.buf[sc.par ^ 1][0][n.c] = pn;
+        a.buf[sc.par ^ 1][1][n.c] = nnew;
+        a.buf[sc.par ^ 1][2][n.c] = snew;
         sP = (double)pn;
         sN = (double)nnew;
     }
-    finish_step<T, 2>(a, t, sP, sN);
+    step_end<T, 2>(a, sc, sP, sN);
 }
 
 }  // namespace tgtk

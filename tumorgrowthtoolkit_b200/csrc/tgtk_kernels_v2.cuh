@@ -45,10 +45,11 @@ template <typename T> __device__ __forceinline__ March march_setup(const StepArg
     return m;
 }
 
-// offset of the own column one plane up (wrapping to plane 0 after plane X-1)
-template <typename T> __device__ __forceinline__ uint32_t march_next(const StepArgs<T> &a, const March &m, int x)
+// offset of a column one plane above plane x (wrapping to plane 0 after plane X-1)
+template <typename T>
+__device__ __forceinline__ uint32_t plane_up(const StepArgs<T> &a, const March &m, uint32_t off, int x)
 {
-    return (x + 1 == a.X) ? m.c - m.wrap_back : m.c + m.sx;
+    return (x + 1 == a.X) ? off - m.wrap_back : off + m.sx;
 }
 
 __device__ __forceinline__ void march_advance(March &m, uint32_t next)
@@ -79,126 +80,168 @@ template <typename T> __device__ __forceinline__ T heaviside50_fast(T s, T sigma
     return T(1) - fast_rcp(T(1) + tg_exp(arg));
 }
 
+// All three kernels are software-pipelined along x: the own-column values of plane x+2 are
+// requested while plane x is computed (they are the loads that miss L1 and come from L2/HBM);
+// the in-plane neighbours of plane x are L1 hits issued at the top of the iteration.  The loop
+// is unrolled three times with the plane roles (current / next / prefetched) rotating through
+// three register sets, so no register moves (which would wait on the prefetch) are needed.
+
 // ---- FK (compact coefficient k, see fk_step_v1) -------------------------------------------
+template <typename T> struct ColFk { T u, k; };
+
 template <typename T> __global__ void __launch_bounds__(256) fk_step_v2(const StepArgs<T> a, const int lx)
 {
-    const int t = a.ctrl->t;
-    if (a.ctrl->stop_reason != 0) return;
-    const T *__restrict__ u = a.buf[t & 1][0];
-    T *__restrict__ o = a.buf[(t + 1) & 1][0];
+    const StepCtl sc = step_begin(a);
+    if (sc.stop) return;
+    const T *__restrict__ u = a.buf[sc.par][0];
+    T *__restrict__ o = a.buf[sc.par ^ 1][0];
     const T *__restrict__ kc = a.coef[0];
     March m = march_setup(a, lx);
     double s = 0.0;
     if (m.x0 < m.x1) {
-        T uc = u[m.c], kk = kc[m.c];
+        ColFk<T> A, B, C;
+        A.u = u[m.c]; A.k = kc[m.c];
         // flux through the face below (x-1 | x); the face above is handed on to the next plane
-        T flux_lo = relu(kc[m.prev] + kk) * (u[m.prev] - uc);
-#pragma unroll 2
-        for (int x = m.x0; x < m.x1; ++x) {
-            const uint32_t nx = march_next(a, m, x);
-            const T up = u[nx], kp = kc[nx];
+        T flux_lo = relu(kc[m.prev] + A.k) * (u[m.prev] - A.u);
+        uint32_t n1 = plane_up(a, m, m.c, m.x0);
+        B.u = u[n1]; B.k = kc[n1];
+        auto step = [&](int x, const ColFk<T> &c, const ColFk<T> &p, ColFk<T> &q) {
+            const int x1 = (x + 1 == a.X) ? 0 : x + 1;
+            const uint32_t n2 = plane_up(a, m, n1, x1);
+            q.u = u[n2]; q.k = kc[n2];                              // prefetch plane x+2
             const T uym = u[m.ym], uyp = u[m.yp], uzm = u[m.zm], uzp = u[m.zp];
             const T kym = kc[m.ym], kyp = kc[m.yp], kzm = kc[m.zm], kzp = kc[m.zp];
-            const T flux_hi = relu(kk + kp) * (uc - up);
+            const T flux_hi = relu(c.k + p.k) * (c.u - p.u);
             T sp = a.cx * (flux_lo - flux_hi);
-            sp += a.cy * (relu(kym + kk) * (uym - uc) - relu(kk + kyp) * (uc - uyp));
-            sp += a.cz * (relu(kzm + kk) * (uzm - uc) - relu(kk + kzp) * (uc - uzp));
-            const T un = uc + a.dt * (sp + a.rho * uc * (T(1) - uc));
+            sp += a.cy * (relu(kym + c.k) * (uym - c.u) - relu(c.k + kyp) * (c.u - uyp));
+            sp += a.cz * (relu(kzm + c.k) * (uzm - c.u) - relu(c.k + kzp) * (c.u - uzp));
+            const T un = c.u + a.dt * (sp + a.rho * c.u * (T(1) - c.u));
             if (m.valid) {
                 o[m.c] = un;
                 s += (double)un;
             }
-            flux_lo = flux_hi; uc = up; kk = kp;
-            march_advance(m, nx);
+            flux_lo = flux_hi;
+            march_advance(m, n1);
+            n1 = n2;
+        };
+        for (int x = m.x0; x < m.x1; x += 3) {
+            step(x, A, B, C);
+            if (x + 1 >= m.x1) break;
+            step(x + 1, B, C, A);
+            if (x + 2 >= m.x1) break;
+            step(x + 2, C, A, B);
         }
     }
-    finish_step<T, 1>(a, t, s, 0.0);
+    step_end<T, 1>(a, sc, s, 0.0);
 }
 
 // ---- FK_DTI: coef[0..2] = D_{x,y,z}(c), reference rounding order (see coef_step_v1 mode 2) -----
+template <typename T> struct ColDti { T u, d0, d1, d2; };
+
 template <typename T> __global__ void __launch_bounds__(256) dti_step_v2(const StepArgs<T> a, const int lx)
 {
     using R = Rn<T>;
-    const int t = a.ctrl->t;
-    if (a.ctrl->stop_reason != 0) return;
-    const T *__restrict__ u = a.buf[t & 1][0];
-    T *__restrict__ o = a.buf[(t + 1) & 1][0];
+    const StepCtl sc = step_begin(a);
+    if (sc.stop) return;
+    const T *__restrict__ u = a.buf[sc.par][0];
+    T *__restrict__ o = a.buf[sc.par ^ 1][0];
     const T *__restrict__ dxa = a.coef[0];
     const T *__restrict__ dya = a.coef[1];
     const T *__restrict__ dza = a.coef[2];
     March m = march_setup(a, lx);
     double s = 0.0;
     if (m.x0 < m.x1) {
-        T um = u[m.prev], uc = u[m.c];
-        for (int x = m.x0; x < m.x1; ++x) {
-            const uint32_t nx = march_next(a, m, x);
-            const T up = u[nx];
-            const T d0 = dxa[m.c], d1 = dya[m.c], d2 = dza[m.c];
+        ColDti<T> A, B, C;
+        T um = u[m.prev];
+        A.u = u[m.c]; A.d0 = dxa[m.c]; A.d1 = dya[m.c]; A.d2 = dza[m.c];
+        uint32_t n1 = plane_up(a, m, m.c, m.x0);
+        B.u = u[n1]; B.d0 = dxa[n1]; B.d1 = dya[n1]; B.d2 = dza[n1];
+        auto step = [&](int x, const ColDti<T> &c, const ColDti<T> &p, ColDti<T> &q) {
+            const int x1 = (x + 1 == a.X) ? 0 : x + 1;
+            const uint32_t n2 = plane_up(a, m, n1, x1);
+            q.u = u[n2]; q.d0 = dxa[n2]; q.d1 = dya[n2]; q.d2 = dza[n2];      // prefetch plane x+2
             const T uym = u[m.ym], uyp = u[m.yp], uzm = u[m.zm], uzp = u[m.zp];
-            const T sx = R::mul(a.cx, R::sub(R::mul(d0, R::sub(um, uc)), R::mul(d0, R::sub(uc, up))));
-            const T sy = R::mul(a.cy, R::sub(R::mul(d1, R::sub(uym, uc)), R::mul(d1, R::sub(uc, uyp))));
-            const T sz = R::mul(a.cz, R::sub(R::mul(d2, R::sub(uzm, uc)), R::mul(d2, R::sub(uc, uzp))));
+            const T sx = R::mul(a.cx, R::sub(R::mul(c.d0, R::sub(um, c.u)), R::mul(c.d0, R::sub(c.u, p.u))));
+            const T sy = R::mul(a.cy, R::sub(R::mul(c.d1, R::sub(uym, c.u)), R::mul(c.d1, R::sub(c.u, uyp))));
+            const T sz = R::mul(a.cz, R::sub(R::mul(c.d2, R::sub(uzm, c.u)), R::mul(c.d2, R::sub(c.u, uzp))));
             const T sp = R::add(R::add(sx, sy), sz);
-            const T un = R::add(uc, R::mul(R::add(sp, R::mul(a.rho, R::mul(uc, R::sub(T(1), uc)))), a.dt));
+            const T un = R::add(c.u, R::mul(R::add(sp, R::mul(a.rho, R::mul(c.u, R::sub(T(1), c.u)))), a.dt));
             if (m.valid) {
                 o[m.c] = un;
                 s += (double)un;
             }
-            um = uc; uc = up;
-            march_advance(m, nx);
+            um = c.u;
+            march_advance(m, n1);
+            n1 = n2;
+        };
+        for (int x = m.x0; x < m.x1; x += 3) {
+            step(x, A, B, C);
+            if (x + 1 >= m.x1) break;
+            step(x + 1, B, C, A);
+            if (x + 2 >= m.x1) break;
+            step(x + 2, C, A, B);
         }
     }
-    finish_step<T, 1>(a, t, s, 0.0);
+    step_end<T, 1>(a, sc, s, 0.0);
 }
 
 // ---- FK_2c (compact coefficients k, b; see fk2c_step_v1) ----------------------------------------
+template <typename T> struct Col2c { T p, n, s, b, k; };   // k: with the necrotic closure applied
+
 template <typename T> __global__ void __launch_bounds__(256) fk2c_step_v2(const StepArgs<T> a, const int lx)
 {
-    const int t = a.ctrl->t;
-    if (a.ctrl->stop_reason != 0) return;
-    const T *__restrict__ P = a.buf[t & 1][0];
-    const T *__restrict__ N = a.buf[t & 1][1];
-    const T *__restrict__ S = a.buf[t & 1][2];
-    T *__restrict__ Po = a.buf[(t + 1) & 1][0];
-    T *__restrict__ No = a.buf[(t + 1) & 1][1];
-    T *__restrict__ So = a.buf[(t + 1) & 1][2];
+    const StepCtl sc = step_begin(a);
+    if (sc.stop) return;
+    const T *__restrict__ P = a.buf[sc.par][0];
+    const T *__restrict__ N = a.buf[sc.par][1];
+    const T *__restrict__ S = a.buf[sc.par][2];
+    T *__restrict__ Po = a.buf[sc.par ^ 1][0];
+    T *__restrict__ No = a.buf[sc.par ^ 1][1];
+    T *__restrict__ So = a.buf[sc.par ^ 1][2];
     const T *__restrict__ kc = a.coef[0];
     const T *__restrict__ bc = a.coef[1];
     March m = march_setup(a, lx);
     const T closed = -Big<T>::v;
     double sP = 0.0, sN = 0.0;
-    // k with the necrotic closure of FK_2c.py:13-15 applied: -Big where P+N > th_necro
-    auto keff = [&](uint32_t q, T pq) { return (pq + N[q] <= a.th_necro) ? kc[q] : closed; };
+    // k with the necrotic closure of FK_2c.py:13-15 applied: -Big where P+N > th_necro.  All
+    // three loads are issued unconditionally so none of them waits for another.
+    auto keff = [&](T pq, T nq, T kq) { return (pq + nq <= a.th_necro) ? kq : closed; };
     if (m.x0 < m.x1) {
-        T p_c = P[m.c], n_c = N[m.c], s_c = S[m.c], b_c = bc[m.c];
-        T k_c = (p_c + n_c <= a.th_necro) ? kc[m.c] : closed;
+        Col2c<T> A, B, C;
+        A.p = P[m.c]; A.n = N[m.c]; A.s = S[m.c]; A.b = bc[m.c]; A.k = keff(A.p, A.n, kc[m.c]);
         // fluxes through the face below (x-1 | x); the face above is handed on to the next plane
         T fp_lo, fs_lo;
         {
             const T p_m = P[m.prev];
-            fp_lo = relu(keff(m.prev, p_m) + k_c) * (p_m - p_c);
-            fs_lo = relu(bc[m.prev] + b_c) * (S[m.prev] - s_c);
+            fp_lo = relu(keff(p_m, N[m.prev], kc[m.prev]) + A.k) * (p_m - A.p);
+            fs_lo = relu(bc[m.prev] + A.b) * (S[m.prev] - A.s);
         }
-#pragma unroll 2
-        for (int x = m.x0; x < m.x1; ++x) {
-            const uint32_t nx = march_next(a, m, x);
-            const T p_p = P[nx], n_p = N[nx], s_p = S[nx], b_p = bc[nx];
-            const T k_p = (p_p + n_p <= a.th_necro) ? kc[nx] : closed;
+        uint32_t n1 = plane_up(a, m, m.c, m.x0);
+        B.p = P[n1]; B.n = N[n1]; B.s = S[n1]; B.b = bc[n1]; B.k = kc[n1];   // B.k raw until its turn
+        auto step = [&](int x, const Col2c<T> &c, Col2c<T> &p, Col2c<T> &q) {
+            const int x1 = (x + 1 == a.X) ? 0 : x + 1;
+            const uint32_t n2 = plane_up(a, m, n1, x1);
+            q.p = P[n2]; q.n = N[n2]; q.s = S[n2]; q.b = bc[n2]; q.k = kc[n2];          // prefetch x+2
             const T pym = P[m.ym], pyp = P[m.yp], pzm = P[m.zm], pzp = P[m.zp];
-            const T kym = keff(m.ym, pym), kyp = keff(m.yp, pyp);
-            const T kzm = keff(m.zm, pzm), kzp = keff(m.zp, pzp);
-            const T fp_hi = relu(k_c + k_p) * (p_c - p_p);
-            const T fs_hi = relu(b_c + b_p) * (s_c - s_p);
+            const T nym = N[m.ym], nyp = N[m.yp], nzm = N[m.zm], nzp = N[m.zp];
+            const T rym = kc[m.ym], ryp = kc[m.yp], rzm = kc[m.zm], rzp = kc[m.zp];
+            const T sym = S[m.ym], syp = S[m.yp], szm = S[m.zm], szp = S[m.zp];
+            const T bym = bc[m.ym], byp = bc[m.yp], bzm = bc[m.zm], bzp = bc[m.zp];
+            // work that needs no in-plane neighbour first: Heaviside, reaction, x faces
+            const T H = heaviside50_fast(c.s, a.sigma_np);
+            p.k = keff(p.p, p.n, p.k);
+            const T fp_hi = relu(c.k + p.k) * (c.p - p.p);
+            const T fs_hi = relu(c.b + p.b) * (c.s - p.s);
+            const T react = a.rho * (c.s * c.p) * ((T(1) - c.p) - c.n) - (a.lambda_np * c.p) * H;
             T sp = a.cx * (fp_lo - fp_hi);
-            sp += a.cy * (relu(kym + k_c) * (pym - p_c) - relu(k_c + kyp) * (p_c - pyp));
-            sp += a.cz * (relu(kzm + k_c) * (pzm - p_c) - relu(k_c + kzp) * (p_c - pzp));
             T ss = a.ex * (fs_lo - fs_hi);
-            ss += a.ey * (relu(bc[m.ym] + b_c) * (S[m.ym] - s_c) - relu(b_c + bc[m.yp]) * (s_c - S[m.yp]));
-            ss += a.ez * (relu(bc[m.zm] + b_c) * (S[m.zm] - s_c) - relu(b_c + bc[m.zp]) * (s_c - S[m.zp]));
-            const T H = heaviside50_fast(s_c, a.sigma_np);
-            const T pn = p_c + a.dt * (sp + a.rho * (s_c * p_c) * ((T(1) - p_c) - n_c) - (a.lambda_np * p_c) * H);
-            const T nn = n_c + a.dt * ((a.lambda_np * pn) * H);
-            const T sn = s_c + a.dt * (ss - (a.lambda_s * s_c) * pn);
+            ss += a.ey * (relu(bym + c.b) * (sym - c.s) - relu(c.b + byp) * (c.s - syp));
+            ss += a.ez * (relu(bzm + c.b) * (szm - c.s) - relu(c.b + bzp) * (c.s - szp));
+            sp += a.cy * (relu(keff(pym, nym, rym) + c.k) * (pym - c.p) - relu(c.k + keff(pyp, nyp, ryp)) * (c.p - pyp));
+            sp += a.cz * (relu(keff(pzm, nzm, rzm) + c.k) * (pzm - c.p) - relu(c.k + keff(pzp, nzp, rzp)) * (c.p - pzp));
+            const T pn = c.p + a.dt * (sp + react);
+            const T nn = c.n + a.dt * ((a.lambda_np * pn) * H);
+            const T sn = c.s + a.dt * (ss - (a.lambda_s * c.s) * pn);
             if (m.valid) {
                 Po[m.c] = pn;
                 No[m.c] = nn;
@@ -207,11 +250,18 @@ template <typename T> __global__ void __launch_bounds__(256) fk2c_step_v2(const 
                 sN += (double)nn;
             }
             fp_lo = fp_hi; fs_lo = fs_hi;
-            p_c = p_p; n_c = n_p; s_c = s_p; b_c = b_p; k_c = k_p;
-            march_advance(m, nx);
+            march_advance(m, n1);
+            n1 = n2;
+        };
+        for (int x = m.x0; x < m.x1; x += 3) {
+            step(x, A, B, C);
+            if (x + 1 >= m.x1) break;
+            step(x + 1, B, C, A);
+            if (x + 2 >= m.x1) break;
+            step(x + 2, C, A, B);
         }
     }
-    finish_step<T, 2>(a, t, sP, sN);
+    step_end<T, 2>(a, sc, sP, sN);
 }
 
 }  // namespace tgtk

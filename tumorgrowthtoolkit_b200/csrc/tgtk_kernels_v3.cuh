@@ -1,0 +1,291 @@
+// Shared-memory staged marching kernels (the default).
+//
+// Same decomposition as tgtk_kernels_v2.cuh -- a block owns a (TY x TZ) column tile and walks
+// LX planes along x, own-column values of planes x, x+1, x+2 live in three rotating register
+// sets -- but the four in-plane neighbours of plane x are read from a shared-memory copy of the
+// plane (tile + a one-voxel ring) instead of L1:
+//   * every global load of the kernel is issued at least one full plane ahead of its first
+//     use (own column: two planes; ring: one plane), so no L2/HBM latency is exposed;
+//   * per-voxel derived quantities (FK_2c: the diffusivity with the necrotic closure applied)
+//     are computed once by the owning thread and shared, not recomputed by four neighbours.
+// The plane copy is double buffered: one __syncthreads() per plane.
+//
+// Out-of-box threads of ragged edge tiles and the ring loaders use periodically wrapped
+// coordinates, so the slot next to the last in-box voxel always holds its np.roll neighbour.
+#pragma once
+#include "tgtk_common.cuh"
+#include "tgtk_kernels_v2.cuh"   // fast_rcp, heaviside50_fast
+
+namespace tgtk {
+
+template <typename T, int TZ> struct TileGeom {
+    // row stride in elements; for 16-wide fp32 rows the two half-warps are put 16 banks apart
+    static constexpr int RS = (sizeof(T) == 4 && TZ == 16) ? 48 : TZ + 2;
+};
+
+struct Stage {
+    int x0, x1;
+    bool valid;          // own column is inside the box (else: a wrapped shadow, nothing stored)
+    bool ring;           // this thread also loads one element of the ring
+    uint32_t c;          // element offset of the own column in plane x
+    uint32_t prev;       // own column in plane x0-1
+    uint32_t h;          // ring element offset in the plane being prefetched
+    uint32_t sx, wrap_back;
+    int so, hs;          // shared-memory slot of the own column / of the ring element
+};
+
+__device__ __forceinline__ int wrap_coord(int v, int n)
+{
+    v %= n;
+    return (v < 0) ? v + n : v;
+}
+
+template <typename T, int TZ, int TY> __device__ __forceinline__ Stage stage_setup(const StepArgs<T> &a, int lx)
+{
+    constexpr int RS = TileGeom<T, TZ>::RS;
+    Stage g;
+    const int tz = threadIdx.x, ty = threadIdx.y, tid = ty * TZ + tz;
+    const int z0 = blockIdx.x * TZ, y0 = blockIdx.y * TY;
+    g.valid = (z0 + tz < a.Z) && (y0 + ty < a.Y);
+    g.x0 = blockIdx.z * lx;
+    g.x1 = min(g.x0 + lx, a.X);
+    g.sx = (uint32_t)a.sx;
+    g.wrap_back = (uint32_t)(a.X - 1) * g.sx;
+    const uint32_t sy = (uint32_t)a.sy, base = (uint32_t)g.x0 * g.sx;
+    g.c = base + (uint32_t)wrap_coord(y0 + ty, a.Y) * sy + (uint32_t)wrap_coord(z0 + tz, a.Z);
+    g.prev = (g.x0 == 0) ? g.c + g.wrap_back : g.c - g.sx;
+    g.so = (ty + 1) * RS + tz + 1;
+    // ring: TZ elements above, TZ below, TY left, TY right
+    int hr = 0, hc = 0;
+    g.ring = tid < 2 * TZ + 2 * TY;
+    if (tid < TZ) { hr = 0; hc = tid + 1; }
+    else if (tid < 2 * TZ) { hr = TY + 1; hc = tid - TZ + 1; }
+    else if (tid < 2 * TZ + TY) { hr = tid - 2 * TZ + 1; hc = 0; }
+    else { hr = tid - 2 * TZ - TY + 1; hc = TZ + 1; }
+    if (!g.ring) { hr = 1; hc = 1; }
+    g.hs = hr * RS + hc;
+    g.h = base + (uint32_t)wrap_coord(y0 - 1 + hr, a.Y) * sy + (uint32_t)wrap_coord(z0 - 1 + hc, a.Z);
+    return g;
+}
+
+template <typename T>
+__device__ __forceinline__ uint32_t stage_up(const StepArgs<T> &a, const Stage &g, uint32_t off, int x)
+{
+    return (x + 1 == a.X) ? off - g.wrap_back : off + g.sx;
+}
+
+// ---- FK_2c ---------------------------------------------------------------------------------------
+template <typename T> struct Col2cS { T p, n, s, b, k; };
+
+template <typename T, int TZ, int TY, int MINB = 2>
+__global__ void __launch_bounds__(TZ *TY, MINB) fk2c_step_v3(const StepArgs<T> a, const int lx)
+{
+    constexpr int RS = TileGeom<T, TZ>::RS, PL = (TY + 2) * RS;
+    __shared__ T tile[2][4][PL];           // [buffer][P, k_eff, S, b][slot]
+    const StepCtl sc = step_begin(a);
+    if (sc.stop) return;
+    const T *__restrict__ P = a.buf[sc.par][0];
+    const T *__restrict__ N = a.buf[sc.par][1];
+    const T *__restrict__ S = a.buf[sc.par][2];
+    T *__restrict__ Po = a.buf[sc.par ^ 1][0];
+    T *__restrict__ No = a.buf[sc.par ^ 1][1];
+    T *__restrict__ So = a.buf[sc.par ^ 1][2];
+    const T *__restrict__ kc = a.coef[0];
+    const T *__restrict__ bc = a.coef[1];
+    Stage g = stage_setup<T, TZ, TY>(a, lx);
+    const T closed = -Big<T>::v;
+    // diffusivity half-coefficient with the necrotic closure of FK_2c.py:13-15 applied
+    auto keff = [&](T pq, T nq, T kq) { return (pq + nq <= a.th_necro) ? kq : closed; };
+    double sP = 0.0, sN = 0.0;
+
+    Col2cS<T> A, B, C;
+    A.p = P[g.c]; A.n = N[g.c]; A.s = S[g.c]; A.b = bc[g.c]; A.k = keff(A.p, A.n, kc[g.c]);
+    T fp_lo, fs_lo;     // fluxes through the face below (x-1 | x); the upper face is handed on
+    {
+        const T p_m = P[g.prev];
+        fp_lo = relu(keff(p_m, N[g.prev], kc[g.prev]) + A.k) * (p_m - A.p);
+        fs_lo = relu(bc[g.prev] + A.b) * (S[g.prev] - A.s);
+    }
+    uint32_t n1 = stage_up(a, g, g.c, g.x0);
+    B.p = P[n1]; B.n = N[n1]; B.s = S[n1]; B.b = bc[n1]; B.k = kc[n1];     // B.k raw until its turn
+    // ring values of the plane about to be published (one register set, refilled right after
+    // it has been stored)
+    T hp = 0, hn = 0, hk = 0, hsv = 0, hb = 0;
+    if (g.ring) { hp = P[g.h]; hn = N[g.h]; hk = kc[g.h]; hsv = S[g.h]; hb = bc[g.h]; }
+    int buf = 0;
+
+    auto step = [&](int x, const Col2cS<T> &c, Col2cS<T> &p, Col2cS<T> &q) {
+        T(*tl)[PL] = tile[buf];
+        // publish plane x
+        tl[0][g.so] = c.p; tl[1][g.so] = c.k; tl[2][g.so] = c.s; tl[3][g.so] = c.b;
+        if (g.ring) {
+            tl[0][g.hs] = hp; tl[1][g.hs] = keff(hp, hn, hk); tl[2][g.hs] = hsv; tl[3][g.hs] = hb;
+        }
+        // request plane x+2 (own column) and the ring of plane x+1
+        const int x1 = (x + 1 == a.X) ? 0 : x + 1;
+        const uint32_t n2 = stage_up(a, g, n1, x1);
+        q.p = P[n2]; q.n = N[n2]; q.s = S[n2]; q.b = bc[n2]; q.k = kc[n2];
+        g.h = stage_up(a, g, g.h, x);
+        if (g.ring) { hp = P[g.h]; hn = N[g.h]; hk = kc[g.h]; hsv = S[g.h]; hb = bc[g.h]; }
+        // work that needs no neighbour: Heaviside, reaction, x faces
+        const T H = heaviside50_fast(c.s, a.sigma_np);
+        p.k = keff(p.p, p.n, p.k);
+        const T fp_hi = relu(c.k + p.k) * (c.p - p.p);
+        const T fs_hi = relu(c.b + p.b) * (c.s - p.s);
+        const T react = a.rho * (c.s * c.p) * ((T(1) - c.p) - c.n) - (a.lambda_np * c.p) * H;
+        T sp = a.cx * (fp_lo - fp_hi);
+        T ss = a.ex * (fs_lo - fs_hi);
+        __syncthreads();
+        const int o = g.so;
+        sp += a.cy * (relu(tl[1][o - RS] + c.k) * (tl[0][o - RS] - c.p) - relu(c.k + tl[1][o + RS]) * (c.p - tl[0][o + RS]));
+        sp += a.cz * (relu(tl[1][o - 1] + c.k) * (tl[0][o - 1] - c.p) - relu(c.k + tl[1][o + 1]) * (c.p - tl[0][o + 1]));
+        ss += a.ey * (relu(tl[3][o - RS] + c.b) * (tl[2][o - RS] - c.s) - relu(c.b + tl[3][o + RS]) * (c.s - tl[2][o + RS]));
+        ss += a.ez * (relu(tl[3][o - 1] + c.b) * (tl[2][o - 1] - c.s) - relu(c.b + tl[3][o + 1]) * (c.s - tl[2][o + 1]));
+        const T pn = c.p + a.dt * (sp + react);
+        const T nn = c.n + a.dt * ((a.lambda_np * pn) * H);
+        const T sn = c.s + a.dt * (ss - (a.lambda_s * c.s) * pn);
+        if (g.valid) {
+            Po[g.c] = pn;
+            No[g.c] = nn;
+            So[g.c] = sn;
+            sP += (double)pn;
+            sN += (double)nn;
+        }
+        fp_lo = fp_hi; fs_lo = fs_hi;
+        g.c = n1; n1 = n2;
+        buf ^= 1;
+    };
+    for (int x = g.x0; x < g.x1; x += 3) {
+        step(x, A, B, C);
+        if (x + 1 >= g.x1) break;
+        step(x + 1, B, C, A);
+        if (x + 2 >= g.x1) break;
+        step(x + 2, C, A, B);
+    }
+    step_end<T, 2>(a, sc, sP, sN);
+}
+
+// ---- FK --------------------------------------------------------------------------------------------
+template <typename T> struct ColFkS { T u, k; };
+
+template <typename T, int TZ, int TY>
+__global__ void __launch_bounds__(TZ *TY) fk_step_v3(const StepArgs<T> a, const int lx)
+{
+    constexpr int RS = TileGeom<T, TZ>::RS, PL = (TY + 2) * RS;
+    __shared__ T tile[2][2][PL];           // [buffer][u, k][slot]
+    const StepCtl sc = step_begin(a);
+    if (sc.stop) return;
+    const T *__restrict__ u = a.buf[sc.par][0];
+    T *__restrict__ out = a.buf[sc.par ^ 1][0];
+    const T *__restrict__ kc = a.coef[0];
+    Stage g = stage_setup<T, TZ, TY>(a, lx);
+    double s = 0.0;
+
+    ColFkS<T> A, B, C;
+    A.u = u[g.c]; A.k = kc[g.c];
+    T flux_lo = relu(kc[g.prev] + A.k) * (u[g.prev] - A.u);
+    uint32_t n1 = stage_up(a, g, g.c, g.x0);
+    B.u = u[n1]; B.k = kc[n1];
+    T hu = 0, hk = 0;
+    if (g.ring) { hu = u[g.h]; hk = kc[g.h]; }
+    int buf = 0;
+
+    auto step = [&](int x, const ColFkS<T> &c, const ColFkS<T> &p, ColFkS<T> &q) {
+        T(*tl)[PL] = tile[buf];
+        tl[0][g.so] = c.u; tl[1][g.so] = c.k;
+        if (g.ring) { tl[0][g.hs] = hu; tl[1][g.hs] = hk; }
+        const int x1 = (x + 1 == a.X) ? 0 : x + 1;
+        const uint32_t n2 = stage_up(a, g, n1, x1);
+        q.u = u[n2]; q.k = kc[n2];
+        g.h = stage_up(a, g, g.h, x);
+        if (g.ring) { hu = u[g.h]; hk = kc[g.h]; }
+        const T flux_hi = relu(c.k + p.k) * (c.u - p.u);
+        T sp = a.cx * (flux_lo - flux_hi);
+        const T react = a.rho * c.u * (T(1) - c.u);
+        __syncthreads();
+        const int o = g.so;
+        sp += a.cy * (relu(tl[1][o - RS] + c.k) * (tl[0][o - RS] - c.u) - relu(c.k + tl[1][o + RS]) * (c.u - tl[0][o + RS]));
+        sp += a.cz * (relu(tl[1][o - 1] + c.k) * (tl[0][o - 1] - c.u) - relu(c.k + tl[1][o + 1]) * (c.u - tl[0][o + 1]));
+        const T un = c.u + a.dt * (sp + react);
+        if (g.valid) {
+            out[g.c] = un;
+            s += (double)un;
+        }
+        flux_lo = flux_hi;
+        g.c = n1; n1 = n2;
+        buf ^= 1;
+    };
+    for (int x = g.x0; x < g.x1; x += 3) {
+        step(x, A, B, C);
+        if (x + 1 >= g.x1) break;
+        step(x + 1, B, C, A);
+        if (x + 2 >= g.x1) break;
+        step(x + 2, C, A, B);
+    }
+    step_end<T, 1>(a, sc, s, 0.0);
+}
+
+// ---- FK_DTI (reference rounding order, see coef_step_v1 mode 2) -------------------------------------
+template <typename T> struct ColDtiS { T u, d0, d1, d2; };
+
+template <typename T, int TZ, int TY>
+__global__ void __launch_bounds__(TZ *TY) dti_step_v3(const StepArgs<T> a, const int lx)
+{
+    using R = Rn<T>;
+    constexpr int RS = TileGeom<T, TZ>::RS, PL = (TY + 2) * RS;
+    __shared__ T tile[2][PL];
+    const StepCtl sc = step_begin(a);
+    if (sc.stop) return;
+    const T *__restrict__ u = a.buf[sc.par][0];
+    T *__restrict__ out = a.buf[sc.par ^ 1][0];
+    const T *__restrict__ dxa = a.coef[0];
+    const T *__restrict__ dya = a.coef[1];
+    const T *__restrict__ dza = a.coef[2];
+    Stage g = stage_setup<T, TZ, TY>(a, lx);
+    double s = 0.0;
+
+    ColDtiS<T> A, B, C;
+    T um = u[g.prev];
+    A.u = u[g.c]; A.d0 = dxa[g.c]; A.d1 = dya[g.c]; A.d2 = dza[g.c];
+    uint32_t n1 = stage_up(a, g, g.c, g.x0);
+    B.u = u[n1]; B.d0 = dxa[n1]; B.d1 = dya[n1]; B.d2 = dza[n1];
+    T hu = 0;
+    if (g.ring) hu = u[g.h];
+    int buf = 0;
+
+    auto step = [&](int x, const ColDtiS<T> &c, const ColDtiS<T> &p, ColDtiS<T> &q) {
+        T *tl = tile[buf];
+        tl[g.so] = c.u;
+        if (g.ring) tl[g.hs] = hu;
+        const int x1 = (x + 1 == a.X) ? 0 : x + 1;
+        const uint32_t n2 = stage_up(a, g, n1, x1);
+        q.u = u[n2]; q.d0 = dxa[n2]; q.d1 = dya[n2]; q.d2 = dza[n2];
+        g.h = stage_up(a, g, g.h, x);
+        if (g.ring) hu = u[g.h];
+        const T sx = R::mul(a.cx, R::sub(R::mul(c.d0, R::sub(um, c.u)), R::mul(c.d0, R::sub(c.u, p.u))));
+        const T react = R::mul(a.rho, R::mul(c.u, R::sub(T(1), c.u)));
+        __syncthreads();
+        const int o = g.so;
+        const T sy = R::mul(a.cy, R::sub(R::mul(c.d1, R::sub(tl[o - RS], c.u)), R::mul(c.d1, R::sub(c.u, tl[o + RS]))));
+        const T sz = R::mul(a.cz, R::sub(R::mul(c.d2, R::sub(tl[o - 1], c.u)), R::mul(c.d2, R::sub(c.u, tl[o + 1]))));
+        const T sp = R::add(R::add(sx, sy), sz);
+        const T un = R::add(c.u, R::mul(R::add(sp, react), a.dt));
+        if (g.valid) {
+            out[g.c] = un;
+            s += (double)un;
+        }
+        um = c.u;
+        g.c = n1; n1 = n2;
+        buf ^= 1;
+    };
+    for (int x = g.x0; x < g.x1; x += 3) {
+        step(x, A, B, C);
+        if (x + 1 >= g.x1) break;
+        step(x + 1, B, C, A);
+        if (x + 2 >= g.x1) break;
+        step(x + 2, C, A, B);
+    }
+    step_end<T, 1>(a, sc, s, 0.0);
+}
+
+}  // namespace tgtk
