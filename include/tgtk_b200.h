@@ -114,6 +114,14 @@ void tgtk_sim_destroy(tgtk_sim *sim);
  * default.  Both compute the same operator. */
 int tgtk_sim_set_variant(tgtk_sim *sim, int variant);
 
+/* Slab decomposition support.  set_sum_range: only planes [x0, x1) of axis 0 count towards the
+ * volume (a rank's owned planes; its ghost planes are stepped but not summed).  buffer_ptr: device
+ * address of ping-pong buffer `which` (0/1) of a state field, so halo planes can be exchanged in
+ * place (NCCL send/recv on views of these buffers); the layout is dense C order (X,Y,Z) of the
+ * simulation's dtype.  After n enqueued steps the current state is buffer n & 1. */
+int tgtk_sim_set_sum_range(tgtk_sim *sim, int x0, int x1);
+int tgtk_sim_buffer_ptr(tgtk_sim *sim, int field, int which, unsigned long long *ptr);
+
 /* Host -> device.  `host` is float64 with element strides (sx,sy,sz); any strides are
  * accepted (rows with sz==1 are copied directly, otherwise gathered on the host).  If
  * `pinned` is non-zero the caller promises page-locked memory and the copy is fully
@@ -168,6 +176,20 @@ int tgtk_faces_host(int device, int X, int Y, int Z, const double *wm, const int
                     const double *gm, const int64_t gm_strides[3], const double *P, const int64_t p_strides[3],
                     const double *N, const int64_t n_strides[3], double th, double th_necro, double Dw,
                     double ratio, int logical_or, int what, double *out_x, double *out_y, double *out_z);
+
+/* Device -> host with restore_tumor + zoom(order=1) applied on the way (FK/FK.py:229-238): the
+ * current state of `field` is placed at `lo` in a zero volume of shape virt_shape and resampled
+ * to out_shape on the device; only the full-resolution result crosses PCIe. */
+int tgtk_sim_download_resampled(tgtk_sim *sim, int field, const int32_t lo[3], const int32_t virt_shape[3], double *out,
+                                const int32_t out_shape[3]);
+
+/* scipy.ndimage.zoom(v, f, order=1) on the device (the resample of FK/FK.py:150-151,233-238).
+ * `v` is a virtual float64 volume of shape virt_shape that is zero except for the box starting
+ * at `lo` that holds `in` (restore_tumor, FK/FK.py:75-90, fused in; pass lo = 0 and
+ * virt_shape = in_shape for a plain zoom).  `out` is dense float64 of out_shape, which the
+ * caller chooses as round(n*f) like scipy does. */
+int tgtk_resample_linear_host(int device, const double *in, const int64_t in_strides[3], const int32_t in_shape[3],
+                              const int32_t lo[3], const int32_t virt_shape[3], double *out, const int32_t out_shape[3]);
 
 #ifdef __cplusplus
 }

@@ -274,3 +274,51 @@ def test_errors_are_reported_not_swallowed(L):
         nat.Sim(nat.make_params(99, nat.F64, (4, 4, 4), (1, 1, 1), 0.1))
     with pytest.raises(nat.NativeError):
         nat.Sim(nat.make_params(nat.MODEL_FK, nat.F64, (0, 4, 4), (1, 1, 1), 0.1))
+
+
+@pytest.mark.parametrize("factor", [0.5, 0.65, 1.0, 2.0, 1.7])
+def test_resample_matches_scipy_zoom(L, factor):
+    """The device resample against scipy.ndimage.zoom(order=1) itself (the reference's call,
+    FK/FK.py:150-151): plain zoom, strided input, and the fused restore_tumor + zoom."""
+    from scipy.ndimage import zoom
+    from tumorgrowthtoolkit_b200 import _host
+    rng = np.random.default_rng(17)
+    a = rng.uniform(0, 1, (23, 31, 18))
+    ref = zoom(a, factor, order=1)
+    got = _host.resample_linear(a, factor)
+    assert got.shape == ref.shape and _maxerr(got, ref) <= 1e-14
+    big = rng.uniform(0, 1, (30, 40, 25))
+    view = big[3:26, 2:33, 5:23]
+    assert _maxerr(_host.resample_linear(view, factor), zoom(view, factor, order=1)) <= 1e-14
+    # crop pasted into zeros, then zoomed back to a "full" grid
+    low_shape = (40, 44, 30)
+    grid = _host.LowResGrid(low_shape, tuple(int(round(n / 0.65)) for n in low_shape), 0.65, 1, 1, 1, (0.5, 0.5, 0.5))
+    box = (np.array([5, 6, 4]), np.array([28, 37, 22]))
+    full = np.zeros(low_shape)
+    full[5:28, 6:37, 4:22] = a
+    ref = zoom(full, grid.up_factor, order=1)
+    got = grid.upsample_crop(a, box)
+    assert got.shape == ref.shape == grid.full_shape and _maxerr(got, ref) <= 1e-14
+
+
+def test_slab_single_rank_equals_plain_loop(L):
+    """world = 1: the slab driver (ghost planes, blocks of `halo` steps, ring closing on the rank
+    itself, volume over owned planes only) must reproduce the plain loop bitwise."""
+    from tumorgrowthtoolkit_b200 import _loop, slab
+    rng = np.random.default_rng(9)
+    shape = (19, 12, 21)
+    wm = rng.uniform(0.2, 0.7, shape)
+    gm = 1.0 - wm
+    u0 = rng.uniform(0, 0.5, shape)
+    args = (u0, wm, gm, 0.1, 1.0, 10.0, 0.3, 0.02, 1.0, 1.1, 0.9, 11)
+    ref = _loop.fk_loop(*args)
+    for halo in (1, 3, 4):
+        got = slab.fk_loop(*args, halo=halo)
+        assert np.array_equal(got["state"], ref["state"]), halo
+        assert abs(got["volume"] - ref["volume"]) <= 1e-12 * ref["volume"]
+    P0, N0, S0 = u0, 0.3 * u0[::-1], np.ones(shape)
+    a2 = (P0, N0, S0, wm, gm, 0.1, 0.9, 1.0, 10.0, 1.3, 0.3, 0.35, 0.5, 0.05, 0.02, 1.0, 1.1, 0.9, 9)
+    ref = _loop.fk2c_loop(*a2)
+    got = slab.fk2c_loop(*a2, halo=2)
+    for k in "PNS":
+        assert np.array_equal(got["state"][k], ref["state"][k]), k

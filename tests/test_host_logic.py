@@ -23,6 +23,17 @@ def cpu_loops(monkeypatch, oracle):
     monkeypatch.setattr(_loop, "fk2c_loop", lambda *a, **kw: oracle.fk2c_loop(*a, **drop(kw)))
     monkeypatch.setattr(_loop, "dti_loop", lambda *a, **kw: oracle.dti_loop(*a, **drop(kw)))
 
+    def cpu_resample(a, out_shape, lo=None, virt_shape=None, device=0):
+        # the device resample replaced by the oracle's (restore_tumor + zoom, FK.py:75-90,233-238)
+        a = np.asarray(a, dtype=np.float64)
+        if virt_shape is not None:
+            full = np.zeros(tuple(int(v) for v in virt_shape))
+            full[tuple(slice(int(l), int(l) + n) for l, n in zip(lo, a.shape))] = a
+            a = full
+        return oracle.zoom_linear(a, out_shape)
+    from tumorgrowthtoolkit_b200 import _host
+    monkeypatch.setattr(_host, "_device_resample", cpu_resample)
+
 
 @pytest.mark.parametrize("name", sorted(FK_CASES))
 def test_fk_solve_host_logic(name, gold_solve, cpu_loops):

@@ -79,8 +79,8 @@ class Solver(BaseSolver):
 
         _host.check_tissue_inputs(gm, wm, pct)
 
-        gm_lo = _host.resample_linear(gm, res_factor)
-        wm_lo = _host.resample_linear(wm, res_factor)
+        gm_lo = _host.resample_linear(gm, res_factor, device=self._device())
+        wm_lo = _host.resample_linear(wm, res_factor, device=self._device())
         grid = _host.LowResGrid(gm_lo.shape, gm.shape, res_factor, *spacing, pct)
         dx, dy, dz = grid.h
 
@@ -110,14 +110,13 @@ class Solver(BaseSolver):
                                 bit_exact=bool(p.get('bit_exact', False)))
             volume = np.float64(run['volume'])
             final_time = run['t_stop'] * dt if run['stop'] == 'volume' else stopping_time
-            final = _host.paste(grid.shape, run['state'], box)
 
-            result['initial_state'] = grid.upsample(initial)
-            result['final_state'] = grid.upsample(final)
+            result['initial_state'] = grid.upsample(initial, device=self._device())
+            result['final_state'] = grid.upsample_crop(run['state'], box, device=self._device())
             result['final_time'] = final_time
             result['final_volume'] = volume
             result['stopping_criteria'] = 'volume' if volume >= stopping_volume else 'time'
-            result['time_series'] = (np.array([grid.upsample(_host.paste(grid.shape, s, box))
+            result['time_series'] = (np.array([grid.upsample_crop(s, box, device=self._device())
                                                for s in run['snapshots']]) if record is not None else None)
             result['Dw'] = Dw
             result['rho'] = rho

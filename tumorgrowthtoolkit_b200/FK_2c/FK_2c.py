@@ -68,8 +68,8 @@ class Solver(FK_Solver):
 
         _host.check_tissue_inputs(gm, wm, pct)
 
-        gm_lo = _host.resample_linear(gm, res_factor)
-        wm_lo = _host.resample_linear(wm, res_factor)
+        gm_lo = _host.resample_linear(gm, res_factor, device=self._device())
+        wm_lo = _host.resample_linear(wm, res_factor, device=self._device())
         grid = _host.LowResGrid(gm_lo.shape, gm.shape, res_factor, *spacing, pct)
         dx, dy, dz = grid.h
 
@@ -93,10 +93,10 @@ class Solver(FK_Solver):
         final_time = run['t_stop'] * dt if run['stop'] == 'volume' else stopping_time
 
         result = {}
-        result['initial_state'] = {k: grid.upsample(v) for k, v in initial.items()}
-        result['final_state'] = {k: grid.upsample(_host.paste(grid.shape, run['state'][k], box)) for k in 'PNS'}
+        result['initial_state'] = {k: grid.upsample(v, device=self._device()) for k, v in initial.items()}
+        result['final_state'] = {k: grid.upsample_crop(run['state'][k], box, device=self._device()) for k in 'PNS'}
         if record is not None:
-            result['time_series'] = {k: [grid.upsample(_host.paste(grid.shape, s, box)) for s in run['snapshots'][k]]
+            result['time_series'] = {k: [grid.upsample_crop(s, box, device=self._device()) for s in run['snapshots'][k]]
                                      for k in 'PNS'}
         else:
             result['time_series'] = None

@@ -58,7 +58,7 @@ class FK_DTI_Solver(FK_Solver):
         assert rgb.ndim == 4, "sRGB must be a 4D numpy array, with the last dimension being 3 (RGB)"
         _host.check_seed(pct)
 
-        rgb_lo = _host.resample_linear(rgb, [res_factor, res_factor, res_factor, 1])
+        rgb_lo = _host.resample_linear(rgb, [res_factor, res_factor, res_factor, 1], device=self._device())
         if doPlot:                                                      # plotting is out of scope
             raise NotImplementedError("doPlot=True needs matplotlib and is not part of the time-stepping path")
         grid = _host.LowResGrid(rgb_lo.shape, rgb.shape, res_factor, *spacing, pct)
@@ -89,14 +89,13 @@ class FK_DTI_Solver(FK_Solver):
                 print("Volume is to small")                             # FK_DTI.py:203-206 (sic)
             volume = np.float64(run['volume'])
             final_time = run['t_stop'] * dt if run['stop'] == 'volume' else stopping_time
-            final = _host.paste(grid.shape, run['state'], box)
 
-            result['initial_state'] = grid.upsample(initial)
-            result['final_state'] = grid.upsample(final)
+            result['initial_state'] = grid.upsample(initial, device=self._device())
+            result['final_state'] = grid.upsample_crop(run['state'], box, device=self._device())
             result['final_time'] = final_time
             result['final_volume'] = volume
             result['stopping_criteria'] = 'volume' if volume >= stopping_volume else 'time'
-            result['time_series'] = (np.array([grid.upsample(_host.paste(grid.shape, s, box))
+            result['time_series'] = (np.array([grid.upsample_crop(s, box, device=self._device())
                                                for s in run['snapshots']]) if record is not None else None)
             result['Dw'] = Dw
             result['rho'] = rho

@@ -10,10 +10,32 @@ import numpy as np
 from scipy.ndimage import zoom as _ndimage_zoom
 
 
-def resample_linear(a, factor):
+def _out_shape(shape, factor):
+    factors = list(factor) if np.ndim(factor) else [factor] * len(shape)
+    return tuple(int(round(n * f)) for n, f in zip(shape, factors))    # scipy's own rule
+
+
+def _device_resample(a, out_shape, lo=None, virt_shape=None, device=0):
+    from . import _ops
+    return _ops.resample_linear(a, out_shape, lo, virt_shape, device)
+
+
+def resample_linear(a, factor, device=0):
     """Trilinear resample with scipy.ndimage.zoom(order=1) semantics (FK/FK.py:150-151,
-    233-238).  The reference resamples on the host; so do we for now."""
-    return _ndimage_zoom(a, factor, order=1)
+    233-238) on the GPU -- 80 % of the reference's solve() wall time is this call (SURVEY.md
+    finding 5).  float64 arrays only; other dtypes (the boolean-mask quirk of SURVEY.md 7) keep
+    scipy's dtype-specific rounding and go through scipy itself."""
+    a = np.asarray(a)
+    if a.dtype != np.float64:
+        return _ndimage_zoom(a, factor, order=1)
+    out_shape = _out_shape(a.shape, factor)
+    if a.ndim == 3:
+        return _device_resample(a, out_shape, device=device)
+    assert a.ndim == 4 and out_shape[3] == a.shape[3], "4-D arrays are resampled per channel"
+    out = np.empty(out_shape, dtype=np.float64)
+    for ch in range(a.shape[3]):
+        out[..., ch] = _device_resample(np.ascontiguousarray(a[..., ch]), out_shape[:3], device=device)
+    return out
 
 
 class LowResGrid:
@@ -27,22 +49,36 @@ class LowResGrid:
         self.h = (dx_mm / res_factor, dy_mm / res_factor, dz_mm / res_factor)  # FK.py:165-167
         self.seed = tuple(int(p * n) for p, n in zip(pct, self.shape))         # FK.py:171-173
 
-    def upsample(self, a):
-        return np.array(resample_linear(a, self.up_factor))
+    def upsample(self, a, device=0):
+        return np.array(resample_linear(a, self.up_factor, device=device))
+
+    def upsample_crop(self, crop_arr, box, device=0):
+        """restore_tumor + zoom back to the input grid in one device pass (FK.py:229-238)."""
+        return _device_resample(crop_arr, _out_shape(self.shape, self.up_factor), lo=box[0], virt_shape=self.shape,
+                                device=device)
 
 
 def seed_gaussian(grid, init_scale):
     """Initial tumour: the clipped Gaussian of FK/FK.py:92-105 centred on the seed voxel
-    (FK.py:191-192): 250/(4*pi*5)^1.5 * exp(-r^2/20), r in mm/init_scale, <=0.1 -> 0, >1 -> 1."""
-    (nx, ny, nz), (dx, dy, dz), (sx, sy, sz) = grid.shape, grid.h, grid.seed
-    x = (np.arange(nx) - sx)[:, None, None] * dx / init_scale
-    y = (np.arange(ny) - sy)[None, :, None] * dy / init_scale
-    z = (np.arange(nz) - sz)[None, None, :] * dz / init_scale
+    (FK.py:191-192): 250/(4*pi*5)^1.5 * exp(-r^2/20), r in mm/init_scale, <=0.1 -> 0, >1 -> 1.
+    Values below the 0.1 cut-off (r > 5.7*init_scale mm) are zero by construction, so only a
+    window around the seed is evaluated; inside it the arithmetic is the reference's."""
+    (nx, ny, nz), h, seed = grid.shape, grid.h, grid.seed
     spread = 5.0
-    g = 250 / np.power(4 * np.pi * spread, 3 / 2) * np.exp(
-        -(np.power(x, 2) + np.power(y, 2) + np.power(z, 2)) / (4 * spread))
+    peak = 250 / np.power(4 * np.pi * spread, 3 / 2)
+    reach = np.sqrt(4 * spread * np.log(peak / 0.1)) * init_scale * 1.001 + 1e-9    # mm
+    out = np.zeros((nx, ny, nz))
+    lo = [max(0, int(np.floor(c - reach / d)) - 1) for c, d in zip(seed, h)]
+    hi = [min(n, int(np.ceil(c + reach / d)) + 2) for c, d, n in zip(seed, h, (nx, ny, nz))]
+    if any(a >= b for a, b in zip(lo, hi)):
+        return out
+    x = (np.arange(lo[0], hi[0]) - seed[0])[:, None, None] * h[0] / init_scale
+    y = (np.arange(lo[1], hi[1]) - seed[1])[None, :, None] * h[1] / init_scale
+    z = (np.arange(lo[2], hi[2]) - seed[2])[None, None, :] * h[2] / init_scale
+    g = peak * np.exp(-(np.power(x, 2) + np.power(y, 2) + np.power(z, 2)) / (4 * spread))
     g = np.where(g > 0.1, g, 0)
-    return np.where(g > 1, np.float64(1), g)
+    out[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = np.where(g > 1, np.float64(1), g)
+    return out
 
 
 def steps_and_dt(nt_float, stopping_time):

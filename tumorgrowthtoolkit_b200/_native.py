@@ -70,6 +70,10 @@ def lib():
     L.tgtk_sim_upload.argtypes = [vp, ctypes.c_int, vp, _I64x3, ctypes.c_int]
     L.tgtk_sim_download.argtypes = [vp, ctypes.c_int, vp, _I64x3]
     L.tgtk_sim_prepare.argtypes = [vp]
+    L.tgtk_sim_set_sum_range.argtypes = [vp, ctypes.c_int, ctypes.c_int]
+    L.tgtk_sim_buffer_ptr.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]
+    i3 = ctypes.c_int32 * 3
+    L.tgtk_sim_download_resampled.argtypes = [vp, ctypes.c_int, i3, i3, vp, i3]
     L.tgtk_sim_set_variant.argtypes = [vp, ctypes.c_int]
     L.tgtk_sim_reset.argtypes = [vp]
     L.tgtk_sim_run.argtypes = [vp, ctypes.c_int, ip, ctypes.c_int]
@@ -164,6 +168,14 @@ class Sim:
     def set_variant(self, variant):
         _check(lib().tgtk_sim_set_variant(self._h, int(variant)))
 
+    def set_sum_range(self, x0, x1):
+        _check(lib().tgtk_sim_set_sum_range(self._h, int(x0), int(x1)))
+
+    def buffer_ptr(self, field, which):
+        ptr = ctypes.c_ulonglong(0)
+        _check(lib().tgtk_sim_buffer_ptr(self._h, int(field), int(which), ctypes.byref(ptr)))
+        return ptr.value
+
     def reset(self):
         _check(lib().tgtk_sim_reset(self._h))
 
@@ -184,6 +196,16 @@ class Sim:
         if out is None:
             out = np.empty(self.shape, dtype=np.float64)
         _check(lib().tgtk_sim_download(self._h, int(field), out.ctypes.data_as(ctypes.c_void_p), _strides(out)))
+        return out
+
+    def download_resampled(self, field, lo, virt_shape, out_shape, out=None):
+        """restore_tumor + zoom(order=1) on the device, then D2H of the full-resolution field."""
+        i3 = ctypes.c_int32 * 3
+        if out is None:
+            out = np.empty(tuple(int(v) for v in out_shape), dtype=np.float64)
+        _check(lib().tgtk_sim_download_resampled(self._h, int(field), i3(*[int(v) for v in lo]),
+                                                 i3(*[int(v) for v in virt_shape]), out.ctypes.data_as(ctypes.c_void_p),
+                                                 i3(*out.shape)))
         return out
 
     def snapshot(self, index, field, out=None):

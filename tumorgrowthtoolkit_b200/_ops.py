@@ -110,3 +110,23 @@ def fk2c_update(P, N, S, D, rho, lambda_np, sigma_np, Ds, lambda_s, dt, dx, dy, 
         if not same:
             dst[...] = b
     return {'P': P, 'N': N, 'S': S}
+
+
+_I32x3 = ctypes.c_int32 * 3
+
+
+def resample_linear(a, out_shape, lo=None, virt_shape=None, device=0):
+    """scipy.ndimage.zoom(v, f, order=1) on the GPU (FK/FK.py:150-151,233-238).  `a` (float64,
+    any strides) fills the box starting at `lo` of a zero volume of shape `virt_shape`
+    (restore_tumor, FK/FK.py:75-90, fused in); plain zoom when lo/virt_shape are omitted."""
+    L = nat.lib()
+    a = nat._as_f64(a)
+    assert a.ndim == 3
+    if virt_shape is None:
+        virt_shape, lo = a.shape, (0, 0, 0)
+    out = np.empty(tuple(int(v) for v in out_shape), dtype=np.float64)
+    rc = L.tgtk_resample_linear_host(int(device), _vp(a), nat._strides(a), _I32x3(*a.shape),
+                                     _I32x3(*[int(v) for v in lo]), _I32x3(*[int(v) for v in virt_shape]),
+                                     _vp(out), _I32x3(*out.shape))
+    nat._check(rc)
+    return out

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -46,6 +47,8 @@ struct tgtk_sim {
     void *state[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     void *coef[12] = {nullptr};
     double *stage = nullptr;  // dense float64 staging for uploads / downloads
+    double *resample_out = nullptr;   // device output of tgtk_sim_download_resampled
+    size_t resample_cap = 0;
     void *initial[3] = {nullptr, nullptr, nullptr};  // state at prepare time (tgtk_sim_reset)
     double *wm = nullptr, *gm = nullptr, *pc = nullptr, *pn = nullptr;
     int faces_what = 0;  // tgtk_faces_host: 0 D_minus, 1 WM_tilda, 2 GM_tilda
@@ -64,6 +67,7 @@ struct tgtk_sim {
     bool use_graph = true;
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // by parity of the first step
     bool host_sched = false;   // no stop criterion: parity baked into launches (see StepArgs)
+    int sum_x0 = 0, sum_x1 = -1;     // planes counted in the volume (-1: all)
     int cur_par = 0, cur_slot = 0;   // launch-time values of StepArgs::par / slot
     int minb = 3;          // FK_2c staged kernel: resident blocks per SM the register budget targets
     unsigned partials_cap = 0;
@@ -73,6 +77,57 @@ struct tgtk_sim {
     bool timed = false;
     int64_t launches = 0;
 };
+
+// Device memory comes from the stream-ordered allocator: unlike cudaMalloc / cudaFree it never
+// synchronises the device, so creating or destroying one simulation does not stall the step
+// kernels of the others that an ensemble keeps in flight on neighbouring streams.
+static cudaError_t sim_malloc(tgtk_sim *s, void **ptr, size_t bytes)
+{
+    return cudaMallocAsync(ptr, bytes ? bytes : 8, s->stream);
+}
+
+static cudaError_t sim_free(tgtk_sim *s, void *ptr)
+{
+    return ptr ? cudaFreeAsync(ptr, s->stream) : cudaSuccess;
+}
+
+// pinned host mirrors of Ctrl are recycled: cudaMallocHost costs far more than a whole small solve
+static std::mutex g_pin_mu;
+static std::vector<Ctrl *> g_pin_free;
+
+static Ctrl *pinned_ctrl_get()
+{
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        if (!g_pin_free.empty()) {
+            Ctrl *c = g_pin_free.back();
+            g_pin_free.pop_back();
+            return c;
+        }
+    }
+    Ctrl *c = nullptr;
+    if (cudaMallocHost(&c, sizeof(Ctrl)) != cudaSuccess) return nullptr;
+    return c;
+}
+
+static void pinned_ctrl_put(Ctrl *c)
+{
+    if (!c) return;
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    g_pin_free.push_back(c);
+}
+
+static void keep_pool_memory(int device)
+{
+    static bool done[64] = {false};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = ~0ull;     // cache freed blocks instead of returning them to the OS
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done[device] = true;
+}
 
 // ------------------------------------------------------------------------------------------
 // layout conversion and coefficient set-up kernels
@@ -192,6 +247,8 @@ template <typename T> static void fill_args(const tgtk_sim *s, StepArgs<T> &a)
     a.host_sched = s->host_sched ? 1 : 0;
     a.par = s->cur_par;
     a.slot = s->cur_slot;
+    a.sum_x0 = s->sum_x0;
+    a.sum_x1 = (s->sum_x1 < 0) ? p.X : s->sum_x1;
 }
 
 template <typename T> static cudaError_t launch_step(tgtk_sim *s)
@@ -324,9 +381,9 @@ static int configure_launch(tgtk_sim *s)
     s->nblocks = s->grid.x * s->grid.y * s->grid.z;
     drop_graph(s);
     if (s->nblocks > s->partials_cap) {
-        if (s->partials) CU(cudaFree(s->partials));
+        if (s->partials) CU(sim_free(s, s->partials));
         s->partials = nullptr;
-        CU(cudaMalloc(&s->partials, sizeof(double) * 2 * s->nblocks * kGraphSteps));   // ring of kGraphSteps slots
+        CU(sim_malloc(s, (void **)(&s->partials), sizeof(double) * 2 * s->nblocks * kGraphSteps));   // ring of kGraphSteps slots
         s->partials_cap = s->nblocks;
     }
     return 0;
@@ -337,12 +394,12 @@ static int ensure_volumes(tgtk_sim *s, int need)
     if (need <= s->volumes_cap) return 0;
     int cap = std::max(need, std::max(1024, s->volumes_cap * 2));
     double *nv = nullptr;
-    CU(cudaMalloc(&nv, sizeof(double) * cap));
+    CU(sim_malloc(s, (void **)(&nv), sizeof(double) * cap));
     CU(cudaMemsetAsync(nv, 0, sizeof(double) * cap, s->stream));
     if (s->volumes) {
         CU(cudaMemcpyAsync(nv, s->volumes, sizeof(double) * s->volumes_cap, cudaMemcpyDeviceToDevice, s->stream));
         CU(cudaStreamSynchronize(s->stream));
-        CU(cudaFree(s->volumes));
+        CU(sim_free(s, s->volumes));
     }
     s->volumes = nv;
     s->volumes_cap = cap;
@@ -397,46 +454,88 @@ static bool dense(const tgtk_sim *s, const int64_t st[3])
     return st[2] == 1 && st[1] == s->p.Z && st[0] == (int64_t)s->p.Y * s->p.Z;
 }
 
-// host (float64, strided) <-> dense device staging
-static int copy_host_stage(tgtk_sim *s, double *host, const int64_t st[3], bool to_device)
+// host (float64, strided) <-> dense float64 device buffer of shape (X,Y,Z)
+static int copy_host_dev(cudaStream_t stream, int X, int Y, int Z, double *dev, double *host, const int64_t st[3],
+                         bool to_device)
 {
-    const tgtk_params &p = s->p;
+    const size_t n = (size_t)X * Y * Z;
     const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
-    if (dense(s, st)) {
-        if (to_device) CU(cudaMemcpyAsync(s->stage, host, s->n * 8, kind, s->stream));
-        else CU(cudaMemcpyAsync(host, s->stage, s->n * 8, kind, s->stream));
+    if (st[2] == 1 && st[1] == Z && st[0] == (int64_t)Y * Z) {
+        if (to_device) CU(cudaMemcpyAsync(dev, host, n * 8, kind, stream));
+        else CU(cudaMemcpyAsync(host, dev, n * 8, kind, stream));
         return 0;
     }
-    if (st[2] == 1 && st[1] >= p.Z && st[0] % st[1] == 0 && st[0] / st[1] >= p.Y) {
+    if (st[2] == 1 && st[1] >= Z && st[0] % st[1] == 0 && st[0] / st[1] >= Y) {
         cudaMemcpy3DParms c;
         memset(&c, 0, sizeof(c));
-        cudaPitchedPtr hp = make_cudaPitchedPtr(host, (size_t)st[1] * 8, (size_t)p.Z * 8, (size_t)(st[0] / st[1]));
-        cudaPitchedPtr dp = make_cudaPitchedPtr(s->stage, (size_t)p.Z * 8, (size_t)p.Z * 8, (size_t)p.Y);
+        cudaPitchedPtr hp = make_cudaPitchedPtr(host, (size_t)st[1] * 8, (size_t)Z * 8, (size_t)(st[0] / st[1]));
+        cudaPitchedPtr dp = make_cudaPitchedPtr(dev, (size_t)Z * 8, (size_t)Z * 8, (size_t)Y);
         c.srcPtr = to_device ? hp : dp;
         c.dstPtr = to_device ? dp : hp;
-        c.extent = make_cudaExtent((size_t)p.Z * 8, (size_t)p.Y, (size_t)p.X);
+        c.extent = make_cudaExtent((size_t)Z * 8, (size_t)Y, (size_t)X);
         c.kind = kind;
-        CU(cudaMemcpy3DAsync(&c, s->stream));
+        CU(cudaMemcpy3DAsync(&c, stream));
         return 0;
     }
     // arbitrary strides: gather / scatter on the host
-    std::vector<double> tmp(s->n);
+    std::vector<double> tmp(n);
     if (to_device) {
         size_t q = 0;
-        for (int i = 0; i < p.X; ++i)
-            for (int j = 0; j < p.Y; ++j)
-                for (int k = 0; k < p.Z; ++k) tmp[q++] = host[i * st[0] + j * st[1] + k * st[2]];
-        CU(cudaMemcpyAsync(s->stage, tmp.data(), s->n * 8, kind, s->stream));
-        CU(cudaStreamSynchronize(s->stream));
+        for (int i = 0; i < X; ++i)
+            for (int j = 0; j < Y; ++j)
+                for (int k = 0; k < Z; ++k) tmp[q++] = host[i * st[0] + j * st[1] + k * st[2]];
+        CU(cudaMemcpyAsync(dev, tmp.data(), n * 8, kind, stream));
+        CU(cudaStreamSynchronize(stream));
     } else {
-        CU(cudaMemcpyAsync(tmp.data(), s->stage, s->n * 8, kind, s->stream));
-        CU(cudaStreamSynchronize(s->stream));
+        CU(cudaMemcpyAsync(tmp.data(), dev, n * 8, kind, stream));
+        CU(cudaStreamSynchronize(stream));
         size_t q = 0;
-        for (int i = 0; i < p.X; ++i)
-            for (int j = 0; j < p.Y; ++j)
-                for (int k = 0; k < p.Z; ++k) host[i * st[0] + j * st[1] + k * st[2]] = tmp[q++];
+        for (int i = 0; i < X; ++i)
+            for (int j = 0; j < Y; ++j)
+                for (int k = 0; k < Z; ++k) host[i * st[0] + j * st[1] + k * st[2]] = tmp[q++];
     }
     return 0;
+}
+
+static int copy_host_stage(tgtk_sim *s, double *host, const int64_t st[3], bool to_device)
+{
+    return copy_host_dev(s->stream, s->p.X, s->p.Y, s->p.Z, s->stage, host, st, to_device);
+}
+
+// scipy.ndimage.zoom(v, f, order=1) of a virtual volume `v` of shape (VX,VY,VZ) that is zero
+// except for the box [lo, lo+in_shape) holding `in` -- i.e. restore_tumor (FK/FK.py:75-90) fused
+// with the resample of FK/FK.py:233-238.  Coordinate map in = out*(n_in-1)/(n_out-1).
+__global__ void resample_linear_kernel(const double *__restrict__ in, int IX, int IY, int IZ, int lx, int ly, int lz,
+                                       int VX, int VY, int VZ, double *__restrict__ out, int OX, int OY, int OZ)
+{
+    const double fx = (OX > 1) ? (double)(VX - 1) / (double)(OX - 1) : 0.0;
+    const double fy = (OY > 1) ? (double)(VY - 1) / (double)(OY - 1) : 0.0;
+    const double fz = (OZ > 1) ? (double)(VZ - 1) / (double)(OZ - 1) : 0.0;
+    const int64_t n = (int64_t)OX * OY * OZ;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(q % OZ);
+        const int64_t r = q / OZ;
+        const int j = (int)(r % OY);
+        const int i = (int)(r / OY);
+        const double xi = i * fx, yj = j * fy, zk = k * fz;
+        int i0 = (int)floor(xi), j0 = (int)floor(yj), k0 = (int)floor(zk);
+        i0 = min(i0, max(VX - 2, 0)); j0 = min(j0, max(VY - 2, 0)); k0 = min(k0, max(VZ - 2, 0));
+        const double tx = xi - i0, ty = yj - j0, tz = zk - k0;
+        double acc = 0.0;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int ii = min(i0 + a, VX - 1) - lx, jj = min(j0 + b, VY - 1) - ly, kk = min(k0 + c, VZ - 1) - lz;
+                    const double w = (a ? tx : 1.0 - tx) * (b ? ty : 1.0 - ty) * (c ? tz : 1.0 - tz);
+                    double v = 0.0;
+                    if (ii >= 0 && ii < IX && jj >= 0 && jj < IY && kk >= 0 && kk < IZ) v = in[((int64_t)ii * IY + jj) * IZ + kk];
+                    acc += w * v;
+                }
+        out[q] = acc;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -461,6 +560,7 @@ int tgtk_sim_create(tgtk_sim **out, const tgtk_params *params, int device, void 
     if (p.dtype != TGTK_F64 && p.dtype != TGTK_F32) return fail("tgtk_sim_create", "unknown dtype");
     if (!(p.h[0] > 0 && p.h[1] > 0 && p.h[2] > 0)) return fail("tgtk_sim_create", "non-positive grid spacing");
     CU(cudaSetDevice(device));
+    keep_pool_memory(device);
     tgtk_sim *s = new (std::nothrow) tgtk_sim();
     if (!s) return fail("tgtk_sim_create", "out of host memory");
     s->p = p;
@@ -494,16 +594,17 @@ int tgtk_sim_create(tgtk_sim **out, const tgtk_params *params, int device, void 
     const size_t bytes = (size_t)p.X * s->sx * s->elem;
     for (int b = 0; b < 2; ++b)
         for (int f = 0; f < s->nfields; ++f) {
-            CU(cudaMalloc(&s->state[b][f], bytes));
+            CU(sim_malloc(s, (void **)(&s->state[b][f]), bytes));
             CU(cudaMemsetAsync(s->state[b][f], 0, bytes, s->stream));
         }
     for (int c = 0; c < s->ncoef; ++c) {
-        CU(cudaMalloc(&s->coef[c], bytes));
+        CU(sim_malloc(s, (void **)(&s->coef[c]), bytes));
         CU(cudaMemsetAsync(s->coef[c], 0, bytes, s->stream));
     }
-    CU(cudaMalloc(&s->stage, s->n * 8));
-    CU(cudaMalloc(&s->ctrl, sizeof(Ctrl)));
-    CU(cudaMallocHost(&s->ctrl_host, sizeof(Ctrl)));
+    CU(sim_malloc(s, (void **)(&s->stage), s->n * 8));
+    CU(sim_malloc(s, (void **)(&s->ctrl), sizeof(Ctrl)));
+    s->ctrl_host = pinned_ctrl_get();
+    if (!s->ctrl_host) return fail("cudaMallocHost", "cannot allocate the pinned control mirror");
     CU(cudaEventCreate(&s->ev0));
     CU(cudaEventCreate(&s->ev1));
     Ctrl init = {0, 0, -1, 0u, 0.0};
@@ -520,19 +621,20 @@ void tgtk_sim_destroy(tgtk_sim *s)
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (int b = 0; b < 2; ++b)
-        for (int f = 0; f < 3; ++f) cudaFree(s->state[b][f]);
-    for (int c = 0; c < 12; ++c) cudaFree(s->coef[c]);
-    for (void *q : s->snaps) cudaFree(q);
-    cudaFree(s->stage);
-    for (int f = 0; f < 3; ++f) cudaFree(s->initial[f]);
-    cudaFree(s->wm);
-    cudaFree(s->gm);
-    cudaFree(s->pc);
-    cudaFree(s->pn);
-    cudaFree(s->ctrl);
-    cudaFree(s->partials);
-    cudaFree(s->volumes);
-    if (s->ctrl_host) cudaFreeHost(s->ctrl_host);
+        for (int f = 0; f < 3; ++f) sim_free(s, s->state[b][f]);
+    for (int c = 0; c < 12; ++c) sim_free(s, s->coef[c]);
+    for (void *q : s->snaps) sim_free(s, q);
+    sim_free(s, s->stage);
+    sim_free(s, s->resample_out);
+    for (int f = 0; f < 3; ++f) sim_free(s, s->initial[f]);
+    sim_free(s, s->wm);
+    sim_free(s, s->gm);
+    sim_free(s, s->pc);
+    sim_free(s, s->pn);
+    sim_free(s, s->ctrl);
+    sim_free(s, s->partials);
+    sim_free(s, s->volumes);
+    pinned_ctrl_put(s->ctrl_host);
     drop_graph(s);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -550,6 +652,25 @@ int tgtk_sim_set_variant(tgtk_sim *s, int variant)
     return configure_launch(s);
 }
 
+int tgtk_sim_set_sum_range(tgtk_sim *s, int x0, int x1)
+{
+    if (!s) return fail("tgtk_sim_set_sum_range", "null argument");
+    if (x0 < 0 || x1 > s->p.X || x0 > x1) return fail("tgtk_sim_set_sum_range", "range outside the box");
+    CU(cudaSetDevice(s->device));
+    s->sum_x0 = x0;
+    s->sum_x1 = x1;
+    drop_graph(s);
+    return 0;
+}
+
+int tgtk_sim_buffer_ptr(tgtk_sim *s, int field, int which, unsigned long long *ptr)
+{
+    if (!s || !ptr) return fail("tgtk_sim_buffer_ptr", "null argument");
+    if (field < 0 || field >= s->nfields || which < 0 || which > 1) return fail("tgtk_sim_buffer_ptr", "no such buffer");
+    *ptr = (unsigned long long)(uintptr_t)s->state[which][field];
+    return 0;
+}
+
 int tgtk_sim_upload(tgtk_sim *s, int field, const double *host, const int64_t strides[3], int pinned)
 {
     (void)pinned;
@@ -561,7 +682,7 @@ int tgtk_sim_upload(tgtk_sim *s, int field, const double *host, const int64_t st
             return fail("tgtk_sim_upload", "model takes no tissue maps");
         double **dst = (field == TGTK_FIELD_WM) ? &s->wm : (field == TGTK_FIELD_GM) ? &s->gm
                        : (field == TGTK_FIELD_PC) ? &s->pc : &s->pn;
-        if (!*dst) CU(cudaMalloc(dst, s->n * 8));
+        if (!*dst) CU(sim_malloc(s, (void **)(dst), s->n * 8));
         if (copy_host_stage(s, const_cast<double *>(host), strides, true)) return 1;
         CU(cudaMemcpyAsync(*dst, s->stage, s->n * 8, cudaMemcpyDeviceToDevice, s->stream));
         s->prepared = false;
@@ -650,10 +771,10 @@ int tgtk_sim_prepare(tgtk_sim *s)
         }
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(s->stream));
-        CU(cudaFree(s->wm));
-        CU(cudaFree(s->gm));
-        CU(cudaFree(s->pc));
-        CU(cudaFree(s->pn));
+        CU(sim_free(s, s->wm));
+        CU(sim_free(s, s->gm));
+        CU(sim_free(s, s->pc));
+        CU(sim_free(s, s->pn));
         s->wm = s->gm = s->pc = s->pn = nullptr;
     }
     // no stop criterion active -> host-scheduled launches (see StepArgs::host_sched)
@@ -668,7 +789,7 @@ int tgtk_sim_prepare(tgtk_sim *s)
     const size_t bytes = (size_t)p.X * s->sx * s->elem;
     const int cur = s->t_enqueued & 1;
     for (int f = 0; f < s->nfields; ++f) {
-        if (!s->initial[f]) CU(cudaMalloc(&s->initial[f], bytes));
+        if (!s->initial[f]) CU(sim_malloc(s, (void **)(&s->initial[f]), bytes));
         CU(cudaMemcpyAsync(s->initial[f], s->state[cur][f], bytes, cudaMemcpyDeviceToDevice, s->stream));
     }
     s->prepared = true;
@@ -687,7 +808,7 @@ int tgtk_sim_reset(tgtk_sim *s)
     Ctrl init = {0, 0, -1, 0u, 0.0};
     *s->ctrl_host = init;
     CU(cudaMemcpyAsync(s->ctrl, s->ctrl_host, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
-    for (void *q : s->snaps) cudaFree(q);
+    for (void *q : s->snaps) sim_free(s, q);
     s->snaps.clear();
     s->snap_steps.clear();
     s->t_enqueued = 0;
@@ -709,7 +830,7 @@ int tgtk_sim_run(tgtk_sim *s, int nsteps, const int32_t *record_steps, int nreco
     for (int i = r; i < nrecord; ++i)
         if (record_steps[i] < s->t_enqueued + nsteps && (i == r || record_steps[i] != record_steps[i - 1])) ++nsnap;
     std::vector<void *> arenas(nsnap, nullptr);
-    for (int i = 0; i < nsnap; ++i) CU(cudaMalloc(&arenas[i], bytes * s->nfields));
+    for (int i = 0; i < nsnap; ++i) CU(sim_malloc(s, (void **)(&arenas[i]), bytes * s->nfields));
     int used = 0;
     CU(cudaEventRecord(s->ev0, s->stream));
     int q = 0;
@@ -750,7 +871,7 @@ int tgtk_sim_run(tgtk_sim *s, int nsteps, const int32_t *record_steps, int nreco
             while (r < nrecord && record_steps[r] == t) ++r;
         }
     }
-    for (int i = used; i < nsnap; ++i) cudaFree(arenas[i]);
+    for (int i = used; i < nsnap; ++i) sim_free(s, arenas[i]);
     CU(cudaEventRecord(s->ev1, s->stream));
     s->timed = true;
     return 0;
@@ -886,6 +1007,75 @@ int tgtk_faces_host(int device, int X, int Y, int Z, const double *wm, const int
     double *outs[3] = {out_x, out_y, out_z};
     for (int a = 0; a < 3 && !rc; ++a) rc = tgtk_sim_download(s, TGTK_FIELD_COEF0 + a, outs[a], dense_st);
     tgtk_sim_destroy(s);
+    return rc;
+}
+
+int tgtk_sim_download_resampled(tgtk_sim *s, int field, const int32_t lo[3], const int32_t virt_shape[3], double *out,
+                                const int32_t out_shape[3])
+{
+    if (!s || !lo || !virt_shape || !out || !out_shape) return fail("tgtk_sim_download_resampled", "null argument");
+    const tgtk_params &p = s->p;
+    const int in_shape[3] = {p.X, p.Y, p.Z};
+    for (int d = 0; d < 3; ++d)
+        if (virt_shape[d] < 1 || out_shape[d] < 1 || lo[d] < 0 || lo[d] + in_shape[d] > virt_shape[d])
+            return fail("tgtk_sim_download_resampled", "bad shape or box");
+    CU(cudaSetDevice(s->device));
+    if (fetch_ctrl(s)) return 1;
+    const void *src = field_ptr(s, field, current_buf(s, nullptr));
+    if (!src) return fail("tgtk_sim_download_resampled", "field not present in this model");
+    if (p.dtype == TGTK_F64)
+        unpack_kernel<double><<<grid_1d(s->n), 256, 0, s->stream>>>((const double *)src, s->stage, p.X, p.Y, p.Z, s->sx, s->sy);
+    else
+        unpack_kernel<float><<<grid_1d(s->n), 256, 0, s->stream>>>((const float *)src, s->stage, p.X, p.Y, p.Z, s->sx, s->sy);
+    CU(cudaGetLastError());
+    const size_t nout = (size_t)out_shape[0] * out_shape[1] * out_shape[2];
+    if (nout > s->resample_cap) {
+        if (s->resample_out) CU(sim_free(s, s->resample_out));
+        s->resample_out = nullptr;
+        s->resample_cap = 0;
+        CU(sim_malloc(s, (void **)(&s->resample_out), nout * 8));
+        s->resample_cap = nout;
+    }
+    resample_linear_kernel<<<grid_1d(nout), 256, 0, s->stream>>>(s->stage, p.X, p.Y, p.Z, lo[0], lo[1], lo[2], virt_shape[0],
+                                                               virt_shape[1], virt_shape[2], s->resample_out, out_shape[0],
+                                                               out_shape[1], out_shape[2]);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, s->resample_out, nout * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int tgtk_resample_linear_host(int device, const double *in, const int64_t in_strides[3], const int32_t in_shape[3],
+                              const int32_t lo[3], const int32_t virt_shape[3], double *out, const int32_t out_shape[3])
+{
+    if (!in || !in_strides || !in_shape || !lo || !virt_shape || !out || !out_shape)
+        return fail("tgtk_resample_linear_host", "null argument");
+    for (int d = 0; d < 3; ++d)
+        if (in_shape[d] < 1 || virt_shape[d] < 1 || out_shape[d] < 1 || lo[d] < 0 || lo[d] + in_shape[d] > virt_shape[d])
+            return fail("tgtk_resample_linear_host", "bad shape or box");
+    CU(cudaSetDevice(device));
+    cudaStream_t st = nullptr;
+    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    const size_t nin = (size_t)in_shape[0] * in_shape[1] * in_shape[2];
+    const size_t nout = (size_t)out_shape[0] * out_shape[1] * out_shape[2];
+    double *din = nullptr, *dout = nullptr;
+    int rc = 0;
+    cudaError_t e = cudaMallocAsync((void **)&din, nin * 8, st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&dout, nout * 8, st);
+    if (e != cudaSuccess) rc = fail("cudaMalloc", cudaGetErrorString(e));
+    if (!rc) rc = copy_host_dev(st, in_shape[0], in_shape[1], in_shape[2], din, const_cast<double *>(in), in_strides, true);
+    if (!rc) {
+        resample_linear_kernel<<<grid_1d(nout), 256, 0, st>>>(din, in_shape[0], in_shape[1], in_shape[2], lo[0], lo[1], lo[2],
+                                                            virt_shape[0], virt_shape[1], virt_shape[2], dout, out_shape[0],
+                                                            out_shape[1], out_shape[2]);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, nout * 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = fail("resample", cudaGetErrorString(e));
+    }
+    if (din) cudaFreeAsync(din, st);
+    if (dout) cudaFreeAsync(dout, st);
+    cudaStreamDestroy(st);
     return rc;
 }
 

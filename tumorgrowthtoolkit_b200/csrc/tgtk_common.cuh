@@ -47,7 +47,14 @@ template <typename T> struct StepArgs {
     // chunk_finish_kernel reduces a whole chunk of steps later -- nothing on the step-to-step
     // critical path depends on a device-side read-modify-write.
     int host_sched, par, slot;
+    // planes [sum_x0, sum_x1) count towards the volume (slab mode: the owned planes, not the ghosts)
+    int sum_x0, sum_x1;
 };
+
+template <typename T> __device__ __forceinline__ bool counts(const StepArgs<T> &a, int x)
+{
+    return x >= a.sum_x0 && x < a.sum_x1;
+}
 
 struct StepCtl {
     int t;       // step index (device-scheduled mode), -1 otherwise

@@ -55,7 +55,7 @@ template <typename T> __global__ void __launch_bounds__(256) fk_step_v1(const St
         sp += a.cz * (fzm * (u[n.zm] - uc) - fzp * (uc - u[n.zp]));
         const T un = uc + a.dt * (sp + a.rho * uc * (T(1) - uc));
         o[n.c] = un;
-        s = (double)un;
+        if (counts(a, i)) s = (double)un;
     }
     step_end<T, 1>(a, sc, s, 0.0);
 }
@@ -94,7 +94,7 @@ template <typename T, int kMode> __global__ void __launch_bounds__(256) coef_ste
         // A += (SP + f*A*(1-A)) * dt
         const T un = R::add(uc, R::mul(R::add(sp, R::mul(a.rho, R::mul(uc, R::sub(T(1), uc)))), a.dt));
         o[n.c] = un;
-        s = (double)un;
+        if (counts(a, i)) s = (double)un;
     }
     step_end<T, 1>(a, sc, s, 0.0);
 }
@@ -140,8 +140,10 @@ template <typename T> __global__ void __launch_bounds__(256) fk2c_step_v1(const 
         Po[n.c] = pn;
         No[n.c] = nnew;
         So[n.c] = snew;
-        sP = (double)pn;
-        sN = (double)nnew;
+        if (counts(a, i)) {
+            sP = (double)pn;
+            sN = (double)nnew;
+        }
     }
     step_end<T, 2>(a, sc, sP, sN);
 }
@@ -180,8 +182,10 @@ template <typename T> __global__ void __launch_bounds__(256) fk2c_coef_step_v1(c
         a.buf[sc.par ^ 1][0][n.c] = pn;
         a.buf[sc.par ^ 1][1][n.c] = nnew;
         a.buf[sc.par ^ 1][2][n.c] = snew;
-        sP = (double)pn;
-        sN = (double)nnew;
+        if (counts(a, i)) {
+            sP = (double)pn;
+            sN = (double)nnew;
+        }
     }
     step_end<T, 2>(a, sc, sP, sN);
 }

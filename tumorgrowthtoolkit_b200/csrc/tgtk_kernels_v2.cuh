@@ -118,7 +118,7 @@ template <typename T> __global__ void __launch_bounds__(256) fk_step_v2(const St
             const T un = c.u + a.dt * (sp + a.rho * c.u * (T(1) - c.u));
             if (m.valid) {
                 o[m.c] = un;
-                s += (double)un;
+                if (counts(a, x)) s += (double)un;
             }
             flux_lo = flux_hi;
             march_advance(m, n1);
@@ -168,7 +168,7 @@ template <typename T> __global__ void __launch_bounds__(256) dti_step_v2(const S
             const T un = R::add(c.u, R::mul(R::add(sp, R::mul(a.rho, R::mul(c.u, R::sub(T(1), c.u)))), a.dt));
             if (m.valid) {
                 o[m.c] = un;
-                s += (double)un;
+                if (counts(a, x)) s += (double)un;
             }
             um = c.u;
             march_advance(m, n1);
@@ -246,8 +246,10 @@ template <typename T> __global__ void __launch_bounds__(256) fk2c_step_v2(const 
                 Po[m.c] = pn;
                 No[m.c] = nn;
                 So[m.c] = sn;
-                sP += (double)pn;
-                sN += (double)nn;
+                if (counts(a, x)) {
+                    sP += (double)pn;
+                    sN += (double)nn;
+                }
             }
             fp_lo = fp_hi; fs_lo = fs_hi;
             march_advance(m, n1);

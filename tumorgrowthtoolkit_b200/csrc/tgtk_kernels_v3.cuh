@@ -148,8 +148,10 @@ __global__ void __launch_bounds__(TZ *TY, MINB) fk2c_step_v3(const StepArgs<T> a
             Po[g.c] = pn;
             No[g.c] = nn;
             So[g.c] = sn;
-            sP += (double)pn;
-            sN += (double)nn;
+            if (counts(a, x)) {
+                sP += (double)pn;
+                sN += (double)nn;
+            }
         }
         fp_lo = fp_hi; fs_lo = fs_hi;
         g.c = n1; n1 = n2;
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(TZ *TY) fk_step_v3(const StepArgs<T> a, const 
         const T un = c.u + a.dt * (sp + react);
         if (g.valid) {
             out[g.c] = un;
-            s += (double)un;
+            if (counts(a, x)) s += (double)un;
         }
         flux_lo = flux_hi;
         g.c = n1; n1 = n2;
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(TZ *TY) dti_step_v3(const StepArgs<T> a, const
         const T un = R::add(c.u, R::mul(R::add(sp, react), a.dt));
         if (g.valid) {
             out[g.c] = un;
-            s += (double)un;
+            if (counts(a, x)) s += (double)un;
         }
         um = c.u;
         g.c = n1; n1 = n2;

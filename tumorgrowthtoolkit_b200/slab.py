@@ -1,0 +1,235 @@
+"""Slab decomposition of one solve over the GPUs of a box (BASELINE.json configs[4]).
+
+The reference has no domain decomposition; this is the spatial analogue of its
+single time loop (FK/FK.py:212-226, FK_2c/FK_2c.py:227-245, FK_DTI/FK_DTI.py:195-214) for grids
+that exceed one GPU's useful working set, e.g. the 2x up-sampled 480x480x310 atlas.
+
+  * axis 0 (slowest, so a halo plane is one contiguous chunk) is split into `world` slabs, one
+    process per GPU; the ring is periodic (rank 0 <-> rank n-1) because the reference's
+    neighbour access is np.roll (SURVEY.md finding 2);
+  * every rank carries `halo` ghost planes on each side and steps its whole extended slab with
+    the ordinary periodic kernels for `halo` time steps between exchanges: after j steps the j
+    outermost ghost planes are stale, the owned planes never are (overlapped halo recompute).
+    One exchange per `halo` steps amortises its latency, which for a 1/8 slab is longer than a
+    step (SURVEY.md 7 "halo latency");
+  * the exchange is in place on the simulation's own device buffers: NCCL send/recv (or gloo in
+    the CPU tests) on views of the owned boundary planes / ghost planes -- no staging copies;
+  * volumes are summed over owned planes only (tgtk_sim_set_sum_range) and all-reduced once.
+
+Only runs without a volume stop criterion are supported here (stopping_volume = inf).
+"""
+import numpy as np
+
+
+class SlabPlan:
+    """Which planes of axis 0 a rank owns and where its halos go (pure host logic)."""
+
+    def __init__(self, X, world, rank, halo):
+        if world < 1 or not (0 <= rank < world):
+            raise ValueError("bad rank / world")
+        base, rem = divmod(int(X), world)
+        sizes = [base + (1 if r < rem else 0) for r in range(world)]
+        if min(sizes) < 1:
+            raise ValueError(f"{X} planes cannot be split over {world} ranks")
+        halo = int(halo)
+        if halo < 1 or halo > min(sizes):
+            raise ValueError(f"halo depth {halo} must be between 1 and the smallest slab ({min(sizes)} planes)")
+        self.X, self.world, self.rank, self.halo, self.sizes = int(X), world, rank, halo, sizes
+        self.x0 = sum(sizes[:rank])
+        self.n = sizes[rank]
+        self.x1 = self.x0 + self.n
+        self.prev, self.next = (rank - 1) % world, (rank + 1) % world
+        self.local_planes = self.n + 2 * halo
+
+    def indices(self):
+        """Global plane index of every local plane (ghosts wrap periodically)."""
+        return np.arange(self.x0 - self.halo, self.x1 + self.halo) % self.X
+
+    def extend(self, a):
+        """Local extended slab (owned planes + ghosts) of a global array split along axis 0."""
+        return np.ascontiguousarray(np.asarray(a)[self.indices()])
+
+    @property
+    def owned(self):
+        return slice(self.halo, self.halo + self.n)
+
+    # local plane ranges of the four halo messages
+    @property
+    def send_up(self):      # my top owned planes -> next rank's lower ghosts
+        return slice(self.n, self.n + self.halo)
+
+    @property
+    def send_down(self):    # my bottom owned planes -> previous rank's upper ghosts
+        return slice(self.halo, 2 * self.halo)
+
+    @property
+    def ghost_lo(self):
+        return slice(0, self.halo)
+
+    @property
+    def ghost_hi(self):
+        return slice(self.halo + self.n, 2 * self.halo + self.n)
+
+
+def exchange_halos(plan, tensors, dist):
+    """In-place ring exchange of `plan.halo` planes per side for every tensor (axis 0 = planes).
+    `dist` is torch.distributed (NCCL on GPU tensors, gloo on CPU tensors) or None when
+    world == 1 (the ring closes on the rank itself: a periodic copy)."""
+    if plan.world == 1:
+        for t in tensors:
+            t[plan.ghost_lo] = t[plan.send_up]
+            t[plan.ghost_hi] = t[plan.send_down]
+        return
+    ops = []
+    for t in tensors:
+        ops.append(dist.P2POp(dist.isend, t[plan.send_up], plan.next))
+        ops.append(dist.P2POp(dist.isend, t[plan.send_down], plan.prev))
+    for t in tensors:
+        ops.append(dist.P2POp(dist.irecv, t[plan.ghost_lo], plan.prev))
+        ops.append(dist.P2POp(dist.irecv, t[plan.ghost_hi], plan.next))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+
+
+def run_blocks(plan, stepper, nsteps, dist):
+    """The decomposed time loop: `halo` steps, one exchange, repeat.  `stepper.run(k)` advances
+    the local extended slab k steps; `stepper.tensors()` returns the current state tensors."""
+    done = 0
+    while done < nsteps:
+        k = min(plan.halo, nsteps - done)
+        stepper.run(k)
+        done += k
+        if done < nsteps:
+            with stepper.context():      # the stream the step kernels run on must be current
+                exchange_halos(plan, stepper.tensors(), dist)
+
+
+class _RawCuda:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
+
+
+class CudaSlabStepper:
+    """One rank's extended slab as a libtgtk_b200 simulation on torch's current CUDA stream."""
+
+    def __init__(self, plan, params, uploads, state_fields, device):
+        import torch
+        from . import _native as nat
+        self.torch, self.nat, self.plan, self.device = torch, nat, plan, device
+        torch.cuda.set_device(device)
+        # a dedicated torch stream: the library launches on it and torch.distributed orders its
+        # NCCL transfers after / before the work of the stream that is current when they are issued
+        self.tstream = torch.cuda.Stream(device=device)
+        self.sim = nat.Sim(params, device, stream=self.tstream.cuda_stream)
+        for field, arr in uploads:
+            self.sim.upload(field, arr)
+        self.sim.prepare()
+        self.sim.set_sum_range(plan.halo, plan.halo + plan.n)
+        self.fields = state_fields
+        self.steps = 0
+        shape = (params.X, params.Y, params.Z)
+        typestr = "<f8" if params.dtype == nat.F64 else "<f4"
+        self.views = {(f, w): torch.as_tensor(_RawCuda(self.sim.buffer_ptr(f, w), shape, typestr), device=f"cuda:{device}")
+                      for f in state_fields for w in (0, 1)}
+
+    def context(self):
+        return self.torch.cuda.stream(self.tstream)
+
+    def run(self, k):
+        self.sim.run(k)
+        self.steps += k
+
+    def tensors(self):
+        return [self.views[(f, self.steps & 1)] for f in self.fields]
+
+    def finish(self):
+        st = self.sim.sync()
+        vols = self.sim.volumes(0, self.steps)
+        owned = {f: self.sim.download(f)[self.plan.owned] for f in self.fields}
+        self.sim.close()
+        return st, vols, owned
+
+
+def gather_planes(plan, own, dist):
+    """All ranks' owned planes (a torch tensor, planes on axis 0) concatenated in rank order on
+    every rank.  Slabs may differ by one plane, all_gather wants equal sizes: pad, then trim."""
+    import torch
+    if plan.world == 1:
+        return own
+    nmax = max(plan.sizes)
+    padded = torch.zeros((nmax,) + tuple(own.shape[1:]), dtype=own.dtype, device=own.device)
+    padded[:own.shape[0]] = own
+    parts = [torch.empty_like(padded) for _ in range(plan.world)]
+    dist.all_gather(parts, padded)
+    return torch.cat([part[:n] for part, n in zip(parts, plan.sizes)], dim=0)
+
+
+def _gather_planes(plan, owned, dist, torch, device):
+    t = torch.from_numpy(np.ascontiguousarray(owned))
+    if plan.world > 1 and device is not None:
+        t = t.to(f"cuda:{device}")
+    return gather_planes(plan, t, dist).cpu().numpy()
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+def _run_cuda(model, fields_in, statics, scalars, shape, h, dt, nsteps, halo, precision, device, names):
+    import torch
+    from . import _native as nat
+    from ._loop import dtype_code
+    dist, rank, world = _dist()
+    plan = SlabPlan(shape[0], world, rank, halo)
+    local_shape = (plan.local_planes,) + tuple(shape[1:])
+    p = nat.make_params(model, dtype_code(precision), local_shape, h, dt, **scalars)
+    uploads = [(f, plan.extend(a)) for f, a in statics] + [(f, plan.extend(a)) for f, a in fields_in]
+    stepper = CudaSlabStepper(plan, p, uploads, [f for f, _ in fields_in], device)
+    # device time of the whole decomposed loop (step kernels + halo exchanges) on this rank
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stepper.tstream)
+    run_blocks(plan, stepper, nsteps, dist)
+    ev1.record(stepper.tstream)
+    st, vols, owned = stepper.finish()
+    loop_ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        v = torch.from_numpy(vols).to(f"cuda:{device}")
+        dist.all_reduce(v)
+        vols = v.cpu().numpy()
+    state = {n: _gather_planes(plan, owned[f], dist, torch, device) for n, (f, _) in zip(names, fields_in)}
+    res = dict(state=state, volume=float(vols[-1]) if len(vols) else None, steps_run=int(nsteps), stop="time",
+               t_stop=None, snapshots=None, volumes=vols, loop_ms=float(loop_ms), plan=plan)
+    if len(names) == 1:
+        res["state"] = state[names[0]]
+    return res
+
+
+def fk_loop(u0, WM, GM, th, Dw, ratio, rho, dt, dx, dy, dz, nsteps, halo=4, precision="fp64", device=0):
+    """FK.py:200,212-226 on a slab-decomposed grid (all ranks pass the same global arrays)."""
+    from . import _native as nat
+    return _run_cuda(nat.MODEL_FK, [(nat.FIELD_U, u0)], [(nat.FIELD_WM, WM), (nat.FIELD_GM, GM)],
+                     dict(rho=rho, Dw=Dw, ratio=ratio, th_matter=th), np.shape(u0), (dx, dy, dz), dt, nsteps, halo,
+                     precision, device, ("u",))
+
+
+def dti_loop(u0, rgb, Dw, rho, dt, dx, dy, dz, nsteps, halo=4, precision="fp64", device=0):
+    """FK_DTI.py:174,195-214 on a slab-decomposed grid (without the `volume < 1e-6` exit)."""
+    from . import _native as nat
+    rgb = np.asarray(rgb)
+    statics = [(nat.FIELD_COEF0 + a, rgb[..., a] * Dw) for a in range(3)]
+    return _run_cuda(nat.MODEL_DTI, [(nat.FIELD_U, u0)], statics, dict(rho=rho, Dw=Dw), np.shape(u0), (dx, dy, dz), dt,
+                     nsteps, halo, precision, device, ("u",))
+
+
+def fk2c_loop(P0, N0, S0, WM, GM, th, th_necro, Dw, ratio, Ds, rho, lambda_np, sigma_np, lambda_s, dt, dx, dy, dz,
+              nsteps, halo=4, precision="fp64", device=0):
+    """FK_2c.py:215-216,227-245 on a slab-decomposed grid: P, N and S halos are exchanged."""
+    from . import _native as nat
+    return _run_cuda(nat.MODEL_FK_2C, [(nat.FIELD_P, P0), (nat.FIELD_N, N0), (nat.FIELD_S, S0)],
+                     [(nat.FIELD_WM, WM), (nat.FIELD_GM, GM)],
+                     dict(rho=rho, Dw=Dw, ratio=ratio, th_matter=th, th_necro=th_necro, Ds=Ds, lambda_np=lambda_np,
+                          sigma_np=sigma_np, lambda_s=lambda_s), np.shape(P0), (dx, dy, dz), dt, nsteps, halo,
+                     precision, device, ("P", "N", "S"))
