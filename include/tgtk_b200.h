@@ -39,8 +39,12 @@ enum tgtk_model {
     TGTK_MODEL_COEF6 = 3,  /* FK_update with six caller-given coefficient arrays   FK/FK.py:34-42 */
     TGTK_MODEL_FK_FACES = 4, /* FK with the three face arrays built in the reference's exact
                                rounding order (bit-exact fp64 mode)    FK/FK.py:10-32 */
-    TGTK_MODEL_FK2C_COEF12 = 5 /* FK_2c_update with twelve caller-given coefficient arrays
+    TGTK_MODEL_FK2C_COEF12 = 5, /* FK_2c_update with twelve caller-given coefficient arrays
                                   FK_2c/FK_2c.py:48-73 */
+    TGTK_MODEL_DTI_FULL = 6 /* opt-in: FK_DTI with all six tensor components (19-point stencil incl.
+                               the mixed derivatives).  NOT in the packaged reference, which keeps
+                               the diagonal only (FK_DTI/tools.py:168-171); parity unpinned.
+                               Fields 20..22 = D_xx,D_yy,D_zz, 23..25 = D_xy,D_xz,D_yz (times Dw). */
 };
 
 enum tgtk_dtype { TGTK_F64 = 0, TGTK_F32 = 1 };

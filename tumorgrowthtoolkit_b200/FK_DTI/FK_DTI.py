@@ -3,7 +3,10 @@
 Same contract as the reference's TumorGrowthToolkit/FK_DTI/FK_DTI.py (class FK_DTI_Solver,
 :21-237).  As in the reference, only the tensor DIAGONAL drives the diffusion and D_plus
 aliases D_minus (:39-45), i.e. the operator is sum_a D_aa(c)*(u[c-1]-2u[c]+u[c+1])/h_a^2.
-Optional extra parameters: precision ('fp64' | 'fp32'), device.
+Optional extra parameters: precision ('fp64' | 'fp32'), device, and
+dti_full_tensor (default False): opt-in 19-point operator that also uses the off-diagonal tensor
+components (mixed derivatives).  The packaged reference has no such mode, so it has no
+reference parity; with zero off-diagonals it equals the reference operator bit for bit.
 """
 import numpy as np
 
@@ -53,6 +56,9 @@ class FK_DTI_Solver(FK_Solver):
         if scaling != 1:                                                # FK_DTI.py:107-110
             tensors = tools.elongate_tensor_along_main_axis_torch(tensors, scaling)
         rgb = tools.makeXYZ_rgb_from_tensor(tensors, exponent=exponent, linear=linear)
+        full_tensor = bool(p.get('dti_full_tensor', False))
+        if full_tensor and (exponent != 1 or linear != 0):
+            raise ValueError("dti_full_tensor needs diffusionTensorExponent=1 and diffusionTensorLinear=0")
 
         assert isinstance(rgb, np.ndarray), "sRGB must be a numpy array"
         assert rgb.ndim == 4, "sRGB must be a 4D numpy array, with the last dimension being 3 (RGB)"
@@ -82,9 +88,17 @@ class FK_DTI_Solver(FK_Solver):
             result['success'] = False
             if not brainmask[grid.seed]:
                 raise ValueError("Origin not within brainmask")
-            run = _loop.dti_loop(_host.crop(initial, box), _host.crop(rgb_lo, box), Dw, rho, dt, dx, dy, dz, nsteps,
-                                 stopping_volume=stopping_volume, record_steps=record,
-                                 precision=p.get('precision', 'fp64'), device=self._device())
+            if full_tensor:
+                off_lo = _host.resample_linear(tools.offdiagonal_from_tensor(tensors),
+                                               [res_factor, res_factor, res_factor, 1], device=self._device())
+                run = _loop.dti_full_loop(_host.crop(initial, box), _host.crop(rgb_lo, box), _host.crop(off_lo, box),
+                                          Dw, rho, dt, dx, dy, dz, nsteps, stopping_volume=stopping_volume,
+                                          record_steps=record, precision=p.get('precision', 'fp64'),
+                                          device=self._device())
+            else:
+                run = _loop.dti_loop(_host.crop(initial, box), _host.crop(rgb_lo, box), Dw, rho, dt, dx, dy, dz, nsteps,
+                                     stopping_volume=stopping_volume, record_steps=record,
+                                     precision=p.get('precision', 'fp64'), device=self._device())
             if run['stop'] == 'small':
                 print("Volume is to small")                             # FK_DTI.py:203-206 (sic)
             volume = np.float64(run['volume'])

@@ -61,6 +61,19 @@ def makeXYZ_rgb_from_tensor(tensor, exponent=1, linear=0):
     return normalise(out)
 
 
+def offdiagonal_from_tensor(tensor):
+    """(X,Y,Z,3) array [D_xy, D_xz, D_yz] in the units of makeXYZ_rgb_from_tensor(tensor, 1, 0):
+    the same two brain-mean normalisations, no clipping (|D_ab| <= sqrt(D_aa D_bb) anyway).
+    Only used by the opt-in `dti_full_tensor` mode, which the reference does not have."""
+    diag = np.stack([tensor[..., a, a] for a in range(3)], axis=-1).astype(np.float64)
+    brain = np.max(diag, axis=-1) > 0
+    m1 = np.mean(diag[brain])
+    d1 = np.clip(diag / m1, 0, 10)
+    m2 = np.mean(d1[brain])
+    off = np.stack([tensor[..., 0, 1], tensor[..., 0, 2], tensor[..., 1, 2]], axis=-1).astype(np.float64)
+    return off / (m1 * m2)
+
+
 def get_RGB(*args, **kwargs):
     """Raw-DWI -> tensor fit with dipy (tools.py:26-89): outside the time-stepping path and
     dipy is not a dependency of this package."""

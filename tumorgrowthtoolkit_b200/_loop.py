@@ -80,6 +80,23 @@ def dti_loop(u0, rgb, Dw, rho, dt, dx, dy, dz, nsteps, stopping_volume=np.inf, r
         return _finish(sim, nsteps, record_steps, (nat.FIELD_U,), ("u",))
 
 
+def dti_full_loop(u0, rgb, offdiag, Dw, rho, dt, dx, dy, dz, nsteps, stopping_volume=np.inf, record_steps=None,
+                  precision="fp64", device=0):
+    """Opt-in full-tensor FK_DTI (NOT in the packaged reference, SURVEY.md finding 1): the
+    reference's diagonal operator plus 2*sum_{a<b} D_ab d_a d_b u on a 19-point stencil.
+    rgb[...,a] = normalised D_aa as in dti_loop; offdiag[...,(xy,xz,yz)] in the same units."""
+    p = nat.make_params(nat.MODEL_DTI_FULL, dtype_code(precision), np.shape(u0), (dx, dy, dz), dt, rho=rho, Dw=Dw,
+                        stopping_volume=stopping_volume, small_volume=0.000001)
+    rgb, offdiag = np.asarray(rgb), np.asarray(offdiag)
+    with nat.Sim(p, device) as sim:
+        for a in range(3):
+            sim.upload(nat.FIELD_COEF0 + a, rgb[..., a] * Dw)
+            sim.upload(nat.FIELD_COEF0 + 3 + a, offdiag[..., a] * Dw)
+        sim.upload(nat.FIELD_U, u0)
+        sim.prepare()
+        return _finish(sim, nsteps, record_steps, (nat.FIELD_U,), ("u",))
+
+
 def fk2c_loop(P0, N0, S0, WM, GM, th, th_necro, Dw, ratio, Ds, rho, lambda_np, sigma_np, lambda_s,
               dt, dx, dy, dz, nsteps, stopping_volume=np.inf, record_steps=None, precision="fp64", device=0):
     """FK_2c: get_D_with_necro + get_D(...,D_s,1) + FK_2c_update fused per step

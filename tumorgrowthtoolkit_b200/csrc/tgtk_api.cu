@@ -234,6 +234,11 @@ template <typename T> static void fill_args(const tgtk_sim *s, StepArgs<T> &a)
     a.cy = (T)(fold ? p.Dw * iy : iy);
     a.cz = (T)(fold ? p.Dw * iz : iz);
     a.ex = (T)(p.Ds * ix); a.ey = (T)(p.Ds * iy); a.ez = (T)(p.Ds * iz);
+    if (p.model == TGTK_MODEL_DTI_FULL) {   // mixed-derivative weights 2/(4 h_a h_b)
+        a.ex = (T)(2.0 / (4.0 * p.h[0] * p.h[1]));
+        a.ey = (T)(2.0 / (4.0 * p.h[0] * p.h[2]));
+        a.ez = (T)(2.0 / (4.0 * p.h[1] * p.h[2]));
+    }
     a.dt = (T)p.dt; a.rho = (T)p.rho;
     a.th_necro = (T)p.th_necro; a.lambda_np = (T)p.lambda_np; a.sigma_np = (T)p.sigma_np; a.lambda_s = (T)p.lambda_s;
     a.vol_scale_p = p.h[0] * p.h[1] * p.h[2];
@@ -296,6 +301,7 @@ template <typename T> static cudaError_t launch_step(tgtk_sim *s)
     case TGTK_MODEL_COEF6: coef_step_v1<T, 0><<<s->grid, s->block, 0, s->stream>>>(a); break;
     case TGTK_MODEL_FK_FACES: coef_step_v1<T, 1><<<s->grid, s->block, 0, s->stream>>>(a); break;
     case TGTK_MODEL_FK2C_COEF12: fk2c_coef_step_v1<T><<<s->grid, s->block, 0, s->stream>>>(a); break;
+    case TGTK_MODEL_DTI_FULL: dti_full_step_v1<T><<<s->grid, s->block, 0, s->stream>>>(a); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -556,7 +562,7 @@ int tgtk_sim_create(tgtk_sim **out, const tgtk_params *params, int device, void 
     if (!out || !params) return fail("tgtk_sim_create", "null argument");
     const tgtk_params &p = *params;
     if (p.X < 1 || p.Y < 1 || p.Z < 1) return fail("tgtk_sim_create", "empty box");
-    if (p.model < 0 || p.model > TGTK_MODEL_FK2C_COEF12) return fail("tgtk_sim_create", "unknown model");
+    if (p.model < 0 || p.model > TGTK_MODEL_DTI_FULL) return fail("tgtk_sim_create", "unknown model");
     if (p.dtype != TGTK_F64 && p.dtype != TGTK_F32) return fail("tgtk_sim_create", "unknown dtype");
     if (!(p.h[0] > 0 && p.h[1] > 0 && p.h[2] > 0)) return fail("tgtk_sim_create", "non-positive grid spacing");
     CU(cudaSetDevice(device));
@@ -584,6 +590,7 @@ int tgtk_sim_create(tgtk_sim **out, const tgtk_params *params, int device, void 
     case TGTK_MODEL_COEF6: s->ncoef = 6; break;
     case TGTK_MODEL_FK_FACES: s->ncoef = 3; break;
     case TGTK_MODEL_FK2C_COEF12: s->ncoef = 12; break;
+    case TGTK_MODEL_DTI_FULL: s->ncoef = 6; break;
     }
     if (const char *v = getenv("TGTK_VARIANT")) s->variant = atoi(v);
     if (const char *v = getenv("TGTK_MINB")) s->minb = atoi(v);
@@ -692,7 +699,7 @@ int tgtk_sim_upload(tgtk_sim *s, int field, const double *host, const int64_t st
     void *dst = field_ptr(s, field, cur);
     if (!dst) return fail("tgtk_sim_upload", "field not present in this model");
     if (field >= TGTK_FIELD_COEF0 && p.model != TGTK_MODEL_DTI && p.model != TGTK_MODEL_COEF6 &&
-        p.model != TGTK_MODEL_FK2C_COEF12)
+        p.model != TGTK_MODEL_FK2C_COEF12 && p.model != TGTK_MODEL_DTI_FULL)
         return fail("tgtk_sim_upload", "coefficient arrays of this model are built by tgtk_sim_prepare");
     if (copy_host_stage(s, const_cast<double *>(host), strides, true)) return 1;
     if (p.dtype == TGTK_F64)

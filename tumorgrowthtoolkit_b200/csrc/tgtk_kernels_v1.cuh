@@ -99,6 +99,50 @@ template <typename T, int kMode> __global__ void __launch_bounds__(256) coef_ste
     step_end<T, 1>(a, sc, s, 0.0);
 }
 
+// ---- FK_DTI with the FULL diffusion tensor (opt-in; NOT in the packaged reference) ------------
+// du/dt = sum_a D_aa d2_a u + 2 sum_{a<b} D_ab d_a d_b u + rho u (1-u): the reference's diagonal
+// operator (FK_DTI/FK_DTI.py:39-45 + FK/FK.py:36-41, evaluated exactly as coef_step_v1 mode 2)
+// plus the mixed-derivative terms on the 12 edge neighbours (19-point stencil),
+//   d_a d_b u = (u[+a,+b] - u[+a,-b] - u[-a,+b] + u[-a,-b]) / (4 h_a h_b).
+// coef[0..2] = D_xx, D_yy, D_zz ; coef[3..5] = D_xy, D_xz, D_yz (all already times Dw).
+// With zero off-diagonals the result equals the reference operator bit for bit.  The only code in
+// the reference that touches off-diagonals is an unpackaged scratch script
+// (FK_DTI/testNewDiffusionStepWithTensor.py:101-119): parity of this mode is unpinned.
+template <typename T> __global__ void __launch_bounds__(256) dti_full_step_v1(const StepArgs<T> a)
+{
+    using R = Rn<T>;
+    const StepCtl sc = step_begin(a);
+    if (sc.stop) return;
+    const T *__restrict__ u = a.buf[sc.par][0];
+    T *__restrict__ o = a.buf[sc.par ^ 1][0];
+    int i, j, k;
+    Nbr n;
+    double s = 0.0;
+    if (voxel_index(a, i, j, k, n)) {
+        const int im = (i == 0) ? a.X - 1 : i - 1, ip = (i + 1 == a.X) ? 0 : i + 1;
+        const int jm = (j == 0) ? a.Y - 1 : j - 1, jp = (j + 1 == a.Y) ? 0 : j + 1;
+        const int km = (k == 0) ? a.Z - 1 : k - 1, kp = (k + 1 == a.Z) ? 0 : k + 1;
+        auto at = [&](int x, int y, int z) { return u[(int64_t)x * a.sx + (int64_t)y * a.sy + z]; };
+        const T uc = u[n.c];
+        const T dxx = a.coef[0][n.c], dyy = a.coef[1][n.c], dzz = a.coef[2][n.c];
+        const T dxy = a.coef[3][n.c], dxz = a.coef[4][n.c], dyz = a.coef[5][n.c];
+        const T sx = R::mul(a.cx, R::sub(R::mul(dxx, R::sub(u[n.xm], uc)), R::mul(dxx, R::sub(uc, u[n.xp]))));
+        const T sy = R::mul(a.cy, R::sub(R::mul(dyy, R::sub(u[n.ym], uc)), R::mul(dyy, R::sub(uc, u[n.yp]))));
+        const T sz = R::mul(a.cz, R::sub(R::mul(dzz, R::sub(u[n.zm], uc)), R::mul(dzz, R::sub(uc, u[n.zp]))));
+        const T sp = R::add(R::add(sx, sy), sz);
+        // mixed terms; ex, ey, ez carry 2/(4 h_x h_y), 2/(4 h_x h_z), 2/(4 h_y h_z)
+        const T mxy = R::sub(R::sub(at(ip, jp, k), at(ip, jm, k)), R::sub(at(im, jp, k), at(im, jm, k)));
+        const T mxz = R::sub(R::sub(at(ip, j, kp), at(ip, j, km)), R::sub(at(im, j, kp), at(im, j, km)));
+        const T myz = R::sub(R::sub(at(i, jp, kp), at(i, jp, km)), R::sub(at(i, jm, kp), at(i, jm, km)));
+        const T cross = R::add(R::add(R::mul(R::mul(a.ex, dxy), mxy), R::mul(R::mul(a.ey, dxz), mxz)),
+                               R::mul(R::mul(a.ez, dyz), myz));
+        const T un = R::add(uc, R::mul(R::add(R::add(sp, cross), R::mul(a.rho, R::mul(uc, R::sub(T(1), uc)))), a.dt));
+        o[n.c] = un;
+        if (counts(a, i)) s = (double)un;
+    }
+    step_end<T, 1>(a, sc, s, 0.0);
+}
+
 // ---- FK_2c, compact coefficients ----------------------------------------------------------
 // coef[0] = k(c)  (P diffusivity half-sum, -Big outside tissue), coef[1] = b(c) = (WM+GM)/2
 // (-Big outside tissue).  The necrotic closure (P+N > th_necro, FK_2c/FK_2c.py:13-15) is

@@ -72,12 +72,38 @@ __device__ __forceinline__ float fast_rcp(float x) { return __frcp_rn(x); }
 // smooth_heaviside (FK_2c.py:75-76) = 1 - 1/(1+e), e = exp(-50 (s - sigma)).  The argument is
 // clamped to +-600 so 1+e stays finite and the reciprocal needs no special cases; for
 // e > 1e260 the reference gives 1 - 1/inf = 1 and so does this.
+// exp(x) for x in [-700, 600] (callers clamp): Cody-Waite reduction x = n ln2 + r, |r| <= ln2/2,
+// degree-12 Taylor polynomial (truncation 1.7e-16 relative), 2^n applied to the exponent field.
+// No range checks and the coefficients come from the constant bank as DFMA operands (libdevice's
+// exp() re-materialises 11 coefficients in uniform registers every call: 22 UMOV per voxel).
+__constant__ double kExpTaylor[11] = {1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,
+                                      1.0 / 40320.0,     1.0 / 5040.0,     1.0 / 720.0,     1.0 / 120.0,
+                                      1.0 / 24.0,        1.0 / 6.0,        0.5};
+
+__device__ __forceinline__ double fast_exp(double x)
+{
+    const double magic = 6755399441055744.0;                      // 1.5 * 2^52: rounds to nearest integer
+    const double t = fma(x, 1.4426950408889634, magic);
+    const int n = __double2loint(t);
+    const double nf = t - magic;
+    double r = fma(nf, -6.93147180369123816490e-01, x);           // ln2 high part
+    r = fma(nf, -1.90821492927058770002e-10, r);                  // ln2 low part
+    double p = kExpTaylor[0];
+#pragma unroll
+    for (int i = 1; i < 11; ++i) p = fma(p, r, kExpTaylor[i]);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+__device__ __forceinline__ float fast_exp(float x) { return expf(x); }
+
 template <typename T> __device__ __forceinline__ T heaviside50_fast(T s, T sigma)
 {
     T arg = T(-50) * (s - sigma);
     arg = (arg > T(600)) ? T(600) : arg;
+    arg = (arg < T(-700)) ? T(-700) : arg;                        // exp < 1e-304: 1 + e == 1 either way
     if (sizeof(T) == 4) arg = (arg > T(80)) ? T(80) : arg;
-    return T(1) - fast_rcp(T(1) + tg_exp(arg));
+    return T(1) - fast_rcp(T(1) + fast_exp(arg));
 }
 
 // All three kernels are software-pipelined along x: the own-column values of plane x+2 are
