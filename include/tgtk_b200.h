@@ -126,6 +126,19 @@ int tgtk_sim_set_variant(tgtk_sim *sim, int variant);
 int tgtk_sim_set_sum_range(tgtk_sim *sim, int x0, int x1);
 int tgtk_sim_buffer_ptr(tgtk_sim *sim, int field, int which, unsigned long long *ptr);
 
+/* Native slab driver (BASELINE.json configs[4]).  The simulation holds one rank's extended slab:
+ * `halo` ghost planes, `owned` planes, `halo` ghost planes along axis 0.  tgtk_sim_run_slab
+ * enqueues the whole decomposed loop on the simulation's stream: blocks of `halo` steps of the
+ * ordinary periodic kernels, each followed by one grouped ncclSend/ncclRecv ring exchange of the
+ * owned boundary planes into the neighbours' ghost planes (in place, no staging).  comm = NULL
+ * closes the ring on the rank itself (one GPU).  NCCL is dlopen'ed; the unique id made on rank 0
+ * travels to the other ranks by any means the caller has (the Python mirror broadcasts it with
+ * torch.distributed).  Only for runs without a stop criterion. */
+int tgtk_nccl_unique_id(char id[128]);
+int tgtk_nccl_comm_create(void **comm, const char id[128], int rank, int world, int device);
+void tgtk_nccl_comm_destroy(void *comm);
+int tgtk_sim_run_slab(tgtk_sim *sim, void *comm, int nsteps, int halo, int owned, int prev, int next);
+
 /* Host -> device.  `host` is float64 with element strides (sx,sy,sz); any strides are
  * accepted (rows with sz==1 are copied directly, otherwise gathered on the host).  If
  * `pinned` is non-zero the caller promises page-locked memory and the copy is fully

@@ -15,6 +15,7 @@ def main():
     ap.add_argument("--halo", type=int, default=4)
     ap.add_argument("--precision", default="fp64")
     ap.add_argument("--factor", type=float, default=2.0)
+    ap.add_argument("--driver", default="native", choices=["native", "torch"])
     ap.add_argument("--check", action="store_true", help="compare with the undecomposed loop on rank 0 (small --steps)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -59,7 +60,7 @@ def main():
         if dist is not None:
             dist.barrier()
         t0 = time.perf_counter()
-        res = call(slab, halo=args.halo)
+        res = call(slab, halo=args.halo, driver=args.driver)
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
@@ -73,7 +74,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         wall, loop_ms = float(t[0]), float(t[1])
     out = {"workload": f"{args.model} slab-decomposed on the {f}x resampled atlas", "box": list(u0.shape),
-           "voxels": int(u0.size), "steps": args.steps, "halo": args.halo, "n_gpus": world, "precision": args.precision,
+           "voxels": int(u0.size), "steps": args.steps, "halo": args.halo, "driver": args.driver, "n_gpus": world, "precision": args.precision,
            "wall_s_incl_setup_and_gather": wall, "loop_ms_max_over_ranks": loop_ms,
            "glups_loop": u0.size * args.steps / (loop_ms * 1e-3) / 1e9 if loop_ms > 0 else None, "final_volume": res["volume"]}
     if args.check and rank == 0:

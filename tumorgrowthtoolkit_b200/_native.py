@@ -70,6 +70,11 @@ def lib():
     L.tgtk_sim_upload.argtypes = [vp, ctypes.c_int, vp, _I64x3, ctypes.c_int]
     L.tgtk_sim_download.argtypes = [vp, ctypes.c_int, vp, _I64x3]
     L.tgtk_sim_prepare.argtypes = [vp]
+    L.tgtk_sim_run_slab.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    L.tgtk_nccl_unique_id.argtypes = [ctypes.c_char_p]
+    L.tgtk_nccl_comm_create.argtypes = [ctypes.POINTER(vp), ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    L.tgtk_nccl_comm_destroy.argtypes = [vp]
+    L.tgtk_nccl_comm_destroy.restype = None
     L.tgtk_sim_set_sum_range.argtypes = [vp, ctypes.c_int, ctypes.c_int]
     L.tgtk_sim_buffer_ptr.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]
     i3 = ctypes.c_int32 * 3
@@ -168,6 +173,9 @@ class Sim:
     def set_variant(self, variant):
         _check(lib().tgtk_sim_set_variant(self._h, int(variant)))
 
+    def run_slab(self, comm, nsteps, halo, owned, prev, nxt):
+        _check(lib().tgtk_sim_run_slab(self._h, comm, int(nsteps), int(halo), int(owned), int(prev), int(nxt)))
+
     def set_sum_range(self, x0, x1):
         _check(lib().tgtk_sim_set_sum_range(self._h, int(x0), int(x1)))
 
@@ -228,3 +236,20 @@ class Sim:
         es = ctypes.c_int(0)
         _check(lib().tgtk_sim_device_ptr(self._h, int(field), ctypes.byref(ptr), pitches, ctypes.byref(es)))
         return ptr.value, tuple(pitches), es.value
+
+
+def nccl_unique_id():
+    buf = ctypes.create_string_buffer(128)
+    _check(lib().tgtk_nccl_unique_id(buf))
+    return buf.raw
+
+
+def nccl_comm_create(uid, rank, world, device):
+    comm = ctypes.c_void_p()
+    _check(lib().tgtk_nccl_comm_create(ctypes.byref(comm), uid, int(rank), int(world), int(device)))
+    return comm
+
+
+def nccl_comm_destroy(comm):
+    if comm:
+        lib().tgtk_nccl_comm_destroy(comm)

@@ -1087,3 +1087,4 @@ int tgtk_resample_linear_host(int device, const double *in, const int64_t in_str
 }
 
 }  // extern "C"
+#include "tgtk_nccl.inc"

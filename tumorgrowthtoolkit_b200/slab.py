@@ -178,7 +178,25 @@ def _dist():
     return None, 0, 1
 
 
-def _run_cuda(model, fields_in, statics, scalars, shape, h, dt, nsteps, halo, precision, device, names):
+_COMMS = {}
+
+
+def _native_comm(dist, rank, world, device):
+    """One NCCL communicator per (world, device) owned by the library; the unique id made on
+    rank 0 is broadcast through the torch.distributed group the caller initialised."""
+    import torch
+    from . import _native as nat
+    key = (world, rank, device)
+    if key not in _COMMS:
+        t = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{device}")
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(nat.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        _COMMS[key] = nat.nccl_comm_create(bytes(t.cpu().numpy().tobytes()), rank, world, device)
+    return _COMMS[key]
+
+
+def _run_cuda(model, fields_in, statics, scalars, shape, h, dt, nsteps, halo, precision, device, names, driver="native"):
     import torch
     from . import _native as nat
     from ._loop import dtype_code
@@ -191,7 +209,13 @@ def _run_cuda(model, fields_in, statics, scalars, shape, h, dt, nsteps, halo, pr
     # device time of the whole decomposed loop (step kernels + halo exchanges) on this rank
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stepper.tstream)
-    run_blocks(plan, stepper, nsteps, dist)
+    if driver == "native":
+        # the whole loop (steps + NCCL ring exchanges) enqueued by the library on the sim's stream
+        comm = _native_comm(dist, rank, world, device) if world > 1 else None
+        stepper.sim.run_slab(comm, nsteps, plan.halo, plan.n, plan.prev, plan.next)
+        stepper.steps = nsteps
+    else:
+        run_blocks(plan, stepper, nsteps, dist)       # torch.distributed send/recv per block
     ev1.record(stepper.tstream)
     st, vols, owned = stepper.finish()
     loop_ms = ev0.elapsed_time(ev1)
@@ -207,29 +231,29 @@ def _run_cuda(model, fields_in, statics, scalars, shape, h, dt, nsteps, halo, pr
     return res
 
 
-def fk_loop(u0, WM, GM, th, Dw, ratio, rho, dt, dx, dy, dz, nsteps, halo=4, precision="fp64", device=0):
+def fk_loop(u0, WM, GM, th, Dw, ratio, rho, dt, dx, dy, dz, nsteps, halo=4, precision="fp64", device=0, driver="native"):
     """FK.py:200,212-226 on a slab-decomposed grid (all ranks pass the same global arrays)."""
     from . import _native as nat
     return _run_cuda(nat.MODEL_FK, [(nat.FIELD_U, u0)], [(nat.FIELD_WM, WM), (nat.FIELD_GM, GM)],
                      dict(rho=rho, Dw=Dw, ratio=ratio, th_matter=th), np.shape(u0), (dx, dy, dz), dt, nsteps, halo,
-                     precision, device, ("u",))
+                     precision, device, ("u",), driver)
 
 
-def dti_loop(u0, rgb, Dw, rho, dt, dx, dy, dz, nsteps, halo=4, precision="fp64", device=0):
+def dti_loop(u0, rgb, Dw, rho, dt, dx, dy, dz, nsteps, halo=4, precision="fp64", device=0, driver="native"):
     """FK_DTI.py:174,195-214 on a slab-decomposed grid (without the `volume < 1e-6` exit)."""
     from . import _native as nat
     rgb = np.asarray(rgb)
     statics = [(nat.FIELD_COEF0 + a, rgb[..., a] * Dw) for a in range(3)]
     return _run_cuda(nat.MODEL_DTI, [(nat.FIELD_U, u0)], statics, dict(rho=rho, Dw=Dw), np.shape(u0), (dx, dy, dz), dt,
-                     nsteps, halo, precision, device, ("u",))
+                     nsteps, halo, precision, device, ("u",), driver)
 
 
 def fk2c_loop(P0, N0, S0, WM, GM, th, th_necro, Dw, ratio, Ds, rho, lambda_np, sigma_np, lambda_s, dt, dx, dy, dz,
-              nsteps, halo=4, precision="fp64", device=0):
+              nsteps, halo=4, precision="fp64", device=0, driver="native"):
     """FK_2c.py:215-216,227-245 on a slab-decomposed grid: P, N and S halos are exchanged."""
     from . import _native as nat
     return _run_cuda(nat.MODEL_FK_2C, [(nat.FIELD_P, P0), (nat.FIELD_N, N0), (nat.FIELD_S, S0)],
                      [(nat.FIELD_WM, WM), (nat.FIELD_GM, GM)],
                      dict(rho=rho, Dw=Dw, ratio=ratio, th_matter=th, th_necro=th_necro, Ds=Ds, lambda_np=lambda_np,
                           sigma_np=sigma_np, lambda_s=lambda_s), np.shape(P0), (dx, dy, dz), dt, nsteps, halo,
-                     precision, device, ("P", "N", "S"))
+                     precision, device, ("P", "N", "S"), driver)
