@@ -113,9 +113,10 @@ int tgtk_device_count(int *count);
 int tgtk_sim_create(tgtk_sim **out, const tgtk_params *params, int device, void *stream);
 void tgtk_sim_destroy(tgtk_sim *sim);
 
-/* Kernel family: 2 (default) = tuned marching kernels, 1 = baseline one-voxel-per-thread
- * kernels kept as the in-device cross-check.  The environment variable TGTK_VARIANT sets the
- * default.  Both compute the same operator. */
+/* Kernel family: 0 (default) = auto, 3 = marching kernels staged through shared memory,
+ * 2 = marching kernels reading neighbours through L1, 1 = baseline one-voxel-per-thread kernels
+ * kept as the in-device cross-check.  The environment variable TGTK_VARIANT sets the default.
+ * All families compute the same operator. */
 int tgtk_sim_set_variant(tgtk_sim *sim, int variant);
 
 /* Slab decomposition support.  set_sum_range: only planes [x0, x1) of axis 0 count towards the

@@ -61,8 +61,9 @@ struct tgtk_sim {
     unsigned nblocks = 0;
     int t_enqueued = 0;
     bool prepared = false;
-    int variant = 3;       // 1: baseline, 2: marching via L1, 3: marching via shared memory (default)
+    int variant = 0;       // 0: auto (default), 1: baseline, 2: marching via L1, 3: marching via shared memory
     int lx = 1;            // planes per block of the marching kernels
+    int pf = 1;            // FK_2c staged kernel: prefetch distance in planes (1: two register sets, 4 blocks/SM; 2: three sets)
     int force_tz = 0;      // 0: pick the tile width by lane waste
     bool use_graph = true;
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // by parity of the first step
@@ -256,11 +257,21 @@ template <typename T> static void fill_args(const tgtk_sim *s, StepArgs<T> &a)
     a.sum_x1 = (s->sum_x1 < 0) ? p.X : s->sum_x1;
 }
 
+// variant 0 = auto: the faster of the two marching families per model and dtype, as measured on
+// B200 at the atlas box: FK fp64 and FK_DTI fp32 through L1 (v2), the rest staged (v3)
+static int effective_variant(const tgtk_sim *s)
+{
+    if (s->variant != 0) return s->variant;
+    if (s->p.model == TGTK_MODEL_FK) return (s->p.dtype == TGTK_F64) ? 2 : 3;
+    if (s->p.model == TGTK_MODEL_DTI) return (s->p.dtype == TGTK_F64) ? 3 : 2;
+    return 3;
+}
+
 template <typename T> static cudaError_t launch_step(tgtk_sim *s)
 {
     StepArgs<T> a;
     fill_args(s, a);
-    if (s->lx > 0 && s->variant == 3) {   // shared-memory staged marching kernels
+    if (s->lx > 0 && effective_variant(s) == 3) {   // shared-memory staged marching kernels
         const bool wide = (s->block.x == 32);
         switch (s->p.model) {
         case TGTK_MODEL_FK:
@@ -268,7 +279,10 @@ template <typename T> static cudaError_t launch_step(tgtk_sim *s)
             else fk_step_v3<T, 16, 16><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
             return cudaGetLastError();
         case TGTK_MODEL_FK_2C:
-            if (s->minb == 4) {
+            if (s->pf == 1) {
+                if (wide) fk2c_step_v3s<T, 32, 8, 4><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+                else fk2c_step_v3s<T, 16, 16, 4><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+            } else if (s->minb == 4) {
                 if (wide) fk2c_step_v3<T, 32, 8, 4><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
                 else fk2c_step_v3<T, 16, 16, 4><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
             } else if (s->minb == 3) {
@@ -321,6 +335,7 @@ template <typename T> static const void *v3_kernel(int model, bool wide, int min
     switch (model) {
     case TGTK_MODEL_FK: return wide ? (const void *)fk_step_v3<T, 32, 8> : (const void *)fk_step_v3<T, 16, 16>;
     case TGTK_MODEL_FK_2C:
+        if (minb == 14) return wide ? (const void *)fk2c_step_v3s<T, 32, 8, 4> : (const void *)fk2c_step_v3s<T, 16, 16, 4>;
         if (minb == 4) return wide ? (const void *)fk2c_step_v3<T, 32, 8, 4> : (const void *)fk2c_step_v3<T, 16, 16, 4>;
         if (minb == 3) return wide ? (const void *)fk2c_step_v3<T, 32, 8, 3> : (const void *)fk2c_step_v3<T, 16, 16, 3>;
         return wide ? (const void *)fk2c_step_v3<T, 32, 8> : (const void *)fk2c_step_v3<T, 16, 16>;
@@ -345,15 +360,16 @@ static int configure_launch(tgtk_sim *s)
 {
     const tgtk_params &p = s->p;
     const bool fits32 = (uint64_t)p.X * (uint64_t)s->sx < (1ull << 31);   // 32-bit element offsets
-    if (s->variant >= 2 && has_v2(p.model) && fits32) {
+    const int variant = effective_variant(s);
+    if (variant >= 2 && has_v2(p.model) && fits32) {
         int best_tz = 32;
         double best = 1e30;
         for (int tz : {64, 32, 16}) {
-            if (s->variant == 3 && tz == 64) continue;   // staged kernels: 32x8 or 16x16 tiles
+            if (variant == 3 && tz == 64) continue;   // staged kernels: 32x8 or 16x16 tiles
             if (s->force_tz && tz != s->force_tz) continue;
             const int ty = 256 / tz;
             const double padded = (double)((p.Z + tz - 1) / tz * tz) * ((p.Y + ty - 1) / ty * ty);
-            const double cost = padded / ((double)p.Z * p.Y) + 0.02 * (tz == 16) + 0.03 * (tz == 64);
+            const double cost = padded / ((double)p.Z * p.Y) + 0.08 * (tz == 16) + 0.03 * (tz == 64);   // full-warp rows measure faster
             if (cost < best) { best = cost; best_tz = tz; }
         }
         const int tz = best_tz, ty = 256 / tz;
@@ -362,8 +378,8 @@ static int configure_launch(tgtk_sim *s)
         // integer) against the two extra planes every segment loads to prime its pipeline.
         int per_sm = 2, sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
-        const void *fn = (s->variant == 3)
-                             ? ((p.dtype == TGTK_F64) ? v3_kernel<double>(p.model, tz == 32, s->minb) : v3_kernel<float>(p.model, tz == 32, s->minb))
+        const void *fn = (variant == 3)
+                             ? ((p.dtype == TGTK_F64) ? v3_kernel<double>(p.model, tz == 32, s->pf == 1 ? 14 : s->minb) : v3_kernel<float>(p.model, tz == 32, s->pf == 1 ? 14 : s->minb))
                              : ((p.dtype == TGTK_F64) ? v2_kernel<double>(p.model) : v2_kernel<float>(p.model));
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
         const double slots = (double)sms * per_sm;
@@ -426,7 +442,7 @@ static cudaError_t launch_one(tgtk_sim *s, int par, int slot)
 static cudaError_t launch_chunk_finish(tgtk_sim *s, int count)
 {
     const tgtk_params &p = s->p;
-    chunk_finish_kernel<<<1, 1024, 0, s->stream>>>(s->ctrl, s->partials, s->volumes, s->volumes_cap, s->nblocks, s->nfields,
+    chunk_finish_kernel<<<count, 256, 0, s->stream>>>(s->ctrl, s->partials, s->volumes, s->volumes_cap, s->nblocks, s->nfields,
                                                    count, p.h[0] * p.h[1] * p.h[2], 1.0);
     return cudaGetLastError();
 }
@@ -594,6 +610,7 @@ int tgtk_sim_create(tgtk_sim **out, const tgtk_params *params, int device, void 
     }
     if (const char *v = getenv("TGTK_VARIANT")) s->variant = atoi(v);
     if (const char *v = getenv("TGTK_MINB")) s->minb = atoi(v);
+    if (const char *v = getenv("TGTK_PF")) s->pf = atoi(v);
     if (const char *v = getenv("TGTK_GRAPH")) s->use_graph = atoi(v) != 0;
     if (const char *v = getenv("TGTK_TZ")) s->force_tz = atoi(v);
     *out = s;  // from here on tgtk_sim_destroy cleans up on failure
@@ -652,7 +669,7 @@ void tgtk_sim_destroy(tgtk_sim *s)
 int tgtk_sim_set_variant(tgtk_sim *s, int variant)
 {
     if (!s) return fail("tgtk_sim_set_variant", "null argument");
-    if (variant < 1 || variant > 3) return fail("tgtk_sim_set_variant", "variant must be 1, 2 or 3");
+    if (variant < 0 || variant > 3) return fail("tgtk_sim_set_variant", "variant must be 0 (auto), 1, 2 or 3");
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(s->stream));
     s->variant = variant;

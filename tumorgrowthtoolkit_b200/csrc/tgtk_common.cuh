@@ -233,37 +233,40 @@ __device__ __forceinline__ void step_end(const StepArgs<T> &a, const StepCtl &c,
     else finish_step<T, kFields>(a, c.t, s0, s1);
 }
 
-// Reduces the partial sums of `count` consecutive host-scheduled steps (ring slots 0..count-1)
-// in a fixed order, logs the volumes and advances the device step counter.  One block.
-__global__ void __launch_bounds__(1024) chunk_finish_kernel(Ctrl *ctrl, const double *partials, double *volumes,
-                                                            int volumes_cap, unsigned nblocks, int nfields, int count,
-                                                            double scale_p, double scale_n)
+// Reduces the partial sums of `count` consecutive host-scheduled steps in a fixed order, logs the
+// volumes and advances the device step counter.  One block per step (ring slot = blockIdx.x); the
+// last block to finish (ticket) publishes the new step index, after every block has read the old.
+__global__ void __launch_bounds__(256) chunk_finish_kernel(Ctrl *ctrl, const double *partials, double *volumes,
+                                                           int volumes_cap, unsigned nblocks, int nfields, int count,
+                                                           double scale_p, double scale_n)
 {
-    __shared__ double red[2][32];
+    __shared__ double red[2][8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int j = blockIdx.x;
     const int t0 = ctrl->t;
-    for (int j = 0; j < count; ++j) {
-        const double *ring = partials + (size_t)j * 2 * nblocks;
-        double v0 = 0.0, v1 = 0.0;
-        for (unsigned i = tid; i < nblocks; i += 1024) {
-            v0 += ring[i];
-            if (nfields > 1) v1 += ring[nblocks + i];
-        }
-        v0 = warp_sum(v0);
-        v1 = warp_sum(v1);
-        __syncthreads();
-        if (lane == 0) { red[0][warp] = v0; red[1][warp] = v1; }
-        __syncthreads();
-        if (tid == 0) {
-            double a0 = 0.0, a1 = 0.0;
-            for (int w = 0; w < 32; ++w) { a0 += red[0][w]; a1 += red[1][w]; }
-            double vol = scale_p * a0;
-            if (nfields > 1) vol += scale_n * a1;
-            if (t0 + j < volumes_cap) volumes[t0 + j] = vol;
-            if (j == count - 1) ctrl->last_volume = vol;
+    const double *ring = partials + (size_t)j * 2 * nblocks;
+    double v0 = 0.0, v1 = 0.0;
+    for (unsigned i = tid; i < nblocks; i += 256) {
+        v0 += ring[i];
+        if (nfields > 1) v1 += ring[nblocks + i];
+    }
+    v0 = warp_sum(v0);
+    v1 = warp_sum(v1);
+    if (lane == 0) { red[0][warp] = v0; red[1][warp] = v1; }
+    __syncthreads();
+    if (tid == 0) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int w = 0; w < 8; ++w) { a0 += red[0][w]; a1 += red[1][w]; }
+        double vol = scale_p * a0;
+        if (nfields > 1) vol += scale_n * a1;
+        if (t0 + j < volumes_cap) volumes[t0 + j] = vol;
+        if (j == count - 1) ctrl->last_volume = vol;
+        __threadfence();
+        if (atomicAdd(&ctrl->ticket, 1u) == (unsigned)count - 1) {
+            ctrl->ticket = 0u;
+            ctrl->t = t0 + count;
         }
     }
-    if (tid == 0) ctrl->t = t0 + count;
 }
 
 }  // namespace tgtk

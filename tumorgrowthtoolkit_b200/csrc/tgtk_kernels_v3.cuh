@@ -23,6 +23,12 @@ template <typename T, int TZ> struct TileGeom {
     static constexpr int RS = (sizeof(T) == 4 && TZ == 16) ? 48 : TZ + 2;
 };
 
+// two fields of one voxel side by side: one 128-bit (fp64) / 64-bit (fp32) shared-memory access
+// per neighbour instead of two
+template <typename T> struct alignas(2 * sizeof(T)) Pair {
+    T a, b;
+};
+
 struct Stage {
     int x0, x1;
     bool valid;          // own column is inside the box (else: a wrapped shadow, nothing stored)
@@ -40,9 +46,9 @@ __device__ __forceinline__ int wrap_coord(int v, int n)
     return (v < 0) ? v + n : v;
 }
 
-template <typename T, int TZ, int TY> __device__ __forceinline__ Stage stage_setup(const StepArgs<T> &a, int lx)
+template <typename T, int TZ, int TY, int RS = TileGeom<T, TZ>::RS>
+__device__ __forceinline__ Stage stage_setup(const StepArgs<T> &a, int lx)
 {
-    constexpr int RS = TileGeom<T, TZ>::RS;
     Stage g;
     const int tz = threadIdx.x, ty = threadIdx.y, tid = ty * TZ + tz;
     const int z0 = blockIdx.x * TZ, y0 = blockIdx.y * TY;
@@ -80,8 +86,8 @@ template <typename T> struct Col2cS { T p, n, s, b, k; };
 template <typename T, int TZ, int TY, int MINB = 2>
 __global__ void __launch_bounds__(TZ *TY, MINB) fk2c_step_v3(const StepArgs<T> a, const int lx)
 {
-    constexpr int RS = TileGeom<T, TZ>::RS, PL = (TY + 2) * RS;
-    __shared__ T tile[2][4][PL];           // [buffer][P, k_eff, S, b][slot]
+    constexpr int RS = TZ + 2, PL = (TY + 2) * RS;
+    __shared__ Pair<T> tile[2][2][PL];     // [buffer][(P, k_eff), (S, b)][slot]
     const StepCtl sc = step_begin(a);
     if (sc.stop) return;
     const T *__restrict__ P = a.buf[sc.par][0];
@@ -92,7 +98,7 @@ __global__ void __launch_bounds__(TZ *TY, MINB) fk2c_step_v3(const StepArgs<T> a
     T *__restrict__ So = a.buf[sc.par ^ 1][2];
     const T *__restrict__ kc = a.coef[0];
     const T *__restrict__ bc = a.coef[1];
-    Stage g = stage_setup<T, TZ, TY>(a, lx);
+    Stage g = stage_setup<T, TZ, TY, RS>(a, lx);
     const T closed = -Big<T>::v;
     // diffusivity half-coefficient with the necrotic closure of FK_2c.py:13-15 applied
     auto keff = [&](T pq, T nq, T kq) { return (pq + nq <= a.th_necro) ? kq : closed; };
@@ -115,11 +121,13 @@ __global__ void __launch_bounds__(TZ *TY, MINB) fk2c_step_v3(const StepArgs<T> a
     int buf = 0;
 
     auto step = [&](int x, const Col2cS<T> &c, Col2cS<T> &p, Col2cS<T> &q) {
-        T(*tl)[PL] = tile[buf];
+        Pair<T>(*tl)[PL] = tile[buf];
         // publish plane x
-        tl[0][g.so] = c.p; tl[1][g.so] = c.k; tl[2][g.so] = c.s; tl[3][g.so] = c.b;
+        tl[0][g.so] = Pair<T>{c.p, c.k};
+        tl[1][g.so] = Pair<T>{c.s, c.b};
         if (g.ring) {
-            tl[0][g.hs] = hp; tl[1][g.hs] = keff(hp, hn, hk); tl[2][g.hs] = hsv; tl[3][g.hs] = hb;
+            tl[0][g.hs] = Pair<T>{hp, keff(hp, hn, hk)};
+            tl[1][g.hs] = Pair<T>{hsv, hb};
         }
         // request plane x+2 (own column) and the ring of plane x+1
         const int x1 = (x + 1 == a.X) ? 0 : x + 1;
@@ -137,10 +145,12 @@ __global__ void __launch_bounds__(TZ *TY, MINB) fk2c_step_v3(const StepArgs<T> a
         T ss = a.ex * (fs_lo - fs_hi);
         __syncthreads();
         const int o = g.so;
-        sp += a.cy * (relu(tl[1][o - RS] + c.k) * (tl[0][o - RS] - c.p) - relu(c.k + tl[1][o + RS]) * (c.p - tl[0][o + RS]));
-        sp += a.cz * (relu(tl[1][o - 1] + c.k) * (tl[0][o - 1] - c.p) - relu(c.k + tl[1][o + 1]) * (c.p - tl[0][o + 1]));
-        ss += a.ey * (relu(tl[3][o - RS] + c.b) * (tl[2][o - RS] - c.s) - relu(c.b + tl[3][o + RS]) * (c.s - tl[2][o + RS]));
-        ss += a.ez * (relu(tl[3][o - 1] + c.b) * (tl[2][o - 1] - c.s) - relu(c.b + tl[3][o + 1]) * (c.s - tl[2][o + 1]));
+        const Pair<T> pym = tl[0][o - RS], pyp = tl[0][o + RS], pzm = tl[0][o - 1], pzp = tl[0][o + 1];   // (P, k)
+        const Pair<T> sym = tl[1][o - RS], syp = tl[1][o + RS], szm = tl[1][o - 1], szp = tl[1][o + 1];   // (S, b)
+        sp += a.cy * (relu(pym.b + c.k) * (pym.a - c.p) - relu(c.k + pyp.b) * (c.p - pyp.a));
+        sp += a.cz * (relu(pzm.b + c.k) * (pzm.a - c.p) - relu(c.k + pzp.b) * (c.p - pzp.a));
+        ss += a.ey * (relu(sym.b + c.b) * (sym.a - c.s) - relu(c.b + syp.b) * (c.s - syp.a));
+        ss += a.ez * (relu(szm.b + c.b) * (szm.a - c.s) - relu(c.b + szp.b) * (c.s - szp.a));
         const T pn = c.p + a.dt * (sp + react);
         const T nn = c.n + a.dt * ((a.lambda_np * pn) * H);
         const T sn = c.s + a.dt * (ss - (a.lambda_s * c.s) * pn);
@@ -167,20 +177,114 @@ __global__ void __launch_bounds__(TZ *TY, MINB) fk2c_step_v3(const StepArgs<T> a
     step_end<T, 2>(a, sc, sP, sN);
 }
 
+// Same kernel with a prefetch distance of ONE plane (two register sets instead of three): the
+// own-column loads of plane x+1 are issued at the top of step x and first used by the x-face flux at
+// its end.  Ten registers fewer per thread -> four resident blocks per SM instead of three.
+template <typename T, int TZ, int TY, int MINB = 4>
+__global__ void __launch_bounds__(TZ *TY, MINB) fk2c_step_v3s(const StepArgs<T> a, const int lx)
+{
+    constexpr int RS = TZ + 2, PL = (TY + 2) * RS;
+    __shared__ Pair<T> tile[2][2][PL];     // [buffer][(P, k_eff), (S, b)][slot]
+    const StepCtl sc = step_begin(a);
+    if (sc.stop) return;
+    const T *__restrict__ P = a.buf[sc.par][0];
+    const T *__restrict__ N = a.buf[sc.par][1];
+    const T *__restrict__ S = a.buf[sc.par][2];
+    T *__restrict__ Po = a.buf[sc.par ^ 1][0];
+    T *__restrict__ No = a.buf[sc.par ^ 1][1];
+    T *__restrict__ So = a.buf[sc.par ^ 1][2];
+    const T *__restrict__ kc = a.coef[0];
+    const T *__restrict__ bc = a.coef[1];
+    Stage g = stage_setup<T, TZ, TY, RS>(a, lx);
+    const T closed = -Big<T>::v;
+    // diffusivity half-coefficient with the necrotic closure of FK_2c.py:13-15 applied
+    auto keff = [&](T pq, T nq, T kq) { return (pq + nq <= a.th_necro) ? kq : closed; };
+    double sP = 0.0, sN = 0.0;
+
+    Col2cS<T> A, B;
+    A.p = P[g.c]; A.n = N[g.c]; A.s = S[g.c]; A.b = bc[g.c]; A.k = keff(A.p, A.n, kc[g.c]);
+    T fp_lo, fs_lo;     // fluxes through the face below (x-1 | x); the upper face is handed on
+    {
+        const T p_m = P[g.prev];
+        fp_lo = relu(keff(p_m, N[g.prev], kc[g.prev]) + A.k) * (p_m - A.p);
+        fs_lo = relu(bc[g.prev] + A.b) * (S[g.prev] - A.s);
+    }
+    // ring values of the plane about to be published (one register set, refilled right after
+    // it has been stored)
+    T hp = 0, hn = 0, hk = 0, hsv = 0, hb = 0;
+    if (g.ring) { hp = P[g.h]; hn = N[g.h]; hk = kc[g.h]; hsv = S[g.h]; hb = bc[g.h]; }
+    int buf = 0;
+
+    auto step = [&](int x, const Col2cS<T> &c, Col2cS<T> &p) {
+        Pair<T>(*tl)[PL] = tile[buf];
+        // publish plane x
+        tl[0][g.so] = Pair<T>{c.p, c.k};
+        tl[1][g.so] = Pair<T>{c.s, c.b};
+        if (g.ring) {
+            tl[0][g.hs] = Pair<T>{hp, keff(hp, hn, hk)};
+            tl[1][g.hs] = Pair<T>{hsv, hb};
+        }
+        // request plane x+1: own column and ring
+        const uint32_t n1 = stage_up(a, g, g.c, x);
+        p.p = P[n1]; p.n = N[n1]; p.s = S[n1]; p.b = bc[n1]; p.k = kc[n1];
+        g.h = stage_up(a, g, g.h, x);
+        if (g.ring) { hp = P[g.h]; hn = N[g.h]; hk = kc[g.h]; hsv = S[g.h]; hb = bc[g.h]; }
+        // work that needs neither neighbours nor plane x+1: Heaviside, reaction
+        const T H = heaviside50_fast(c.s, a.sigma_np);
+        const T react = a.rho * (c.s * c.p) * ((T(1) - c.p) - c.n) - (a.lambda_np * c.p) * H;
+        T sp = T(0), ss = T(0);
+        __syncthreads();
+        const int o = g.so;
+        const Pair<T> pym = tl[0][o - RS], pyp = tl[0][o + RS], pzm = tl[0][o - 1], pzp = tl[0][o + 1];   // (P, k)
+        const Pair<T> sym = tl[1][o - RS], syp = tl[1][o + RS], szm = tl[1][o - 1], szp = tl[1][o + 1];   // (S, b)
+        sp += a.cy * (relu(pym.b + c.k) * (pym.a - c.p) - relu(c.k + pyp.b) * (c.p - pyp.a));
+        sp += a.cz * (relu(pzm.b + c.k) * (pzm.a - c.p) - relu(c.k + pzp.b) * (c.p - pzp.a));
+        ss += a.ey * (relu(sym.b + c.b) * (sym.a - c.s) - relu(c.b + syp.b) * (c.s - syp.a));
+        ss += a.ez * (relu(szm.b + c.b) * (szm.a - c.s) - relu(c.b + szp.b) * (c.s - szp.a));
+        // x faces last: plane x+1 has had the whole step to arrive
+        p.k = keff(p.p, p.n, p.k);
+        const T fp_hi = relu(c.k + p.k) * (c.p - p.p);
+        const T fs_hi = relu(c.b + p.b) * (c.s - p.s);
+        sp += a.cx * (fp_lo - fp_hi);
+        ss += a.ex * (fs_lo - fs_hi);
+        const T pn = c.p + a.dt * (sp + react);
+        const T nn = c.n + a.dt * ((a.lambda_np * pn) * H);
+        const T sn = c.s + a.dt * (ss - (a.lambda_s * c.s) * pn);
+        if (g.valid) {
+            Po[g.c] = pn;
+            No[g.c] = nn;
+            So[g.c] = sn;
+            if (counts(a, x)) {
+                sP += (double)pn;
+                sN += (double)nn;
+            }
+        }
+        fp_lo = fp_hi; fs_lo = fs_hi;
+        g.c = n1;
+        buf ^= 1;
+    };
+    for (int x = g.x0; x < g.x1; x += 2) {
+        step(x, A, B);
+        if (x + 1 >= g.x1) break;
+        step(x + 1, B, A);
+    }
+    step_end<T, 2>(a, sc, sP, sN);
+}
+
 // ---- FK --------------------------------------------------------------------------------------------
 template <typename T> struct ColFkS { T u, k; };
 
 template <typename T, int TZ, int TY>
 __global__ void __launch_bounds__(TZ *TY) fk_step_v3(const StepArgs<T> a, const int lx)
 {
-    constexpr int RS = TileGeom<T, TZ>::RS, PL = (TY + 2) * RS;
-    __shared__ T tile[2][2][PL];           // [buffer][u, k][slot]
+    constexpr int RS = TZ + 2, PL = (TY + 2) * RS;
+    __shared__ Pair<T> tile[2][PL];        // [buffer][slot] of (u, k)
     const StepCtl sc = step_begin(a);
     if (sc.stop) return;
     const T *__restrict__ u = a.buf[sc.par][0];
     T *__restrict__ out = a.buf[sc.par ^ 1][0];
     const T *__restrict__ kc = a.coef[0];
-    Stage g = stage_setup<T, TZ, TY>(a, lx);
+    Stage g = stage_setup<T, TZ, TY, RS>(a, lx);
     double s = 0.0;
 
     ColFkS<T> A, B, C;
@@ -193,9 +297,9 @@ __global__ void __launch_bounds__(TZ *TY) fk_step_v3(const StepArgs<T> a, const 
     int buf = 0;
 
     auto step = [&](int x, const ColFkS<T> &c, const ColFkS<T> &p, ColFkS<T> &q) {
-        T(*tl)[PL] = tile[buf];
-        tl[0][g.so] = c.u; tl[1][g.so] = c.k;
-        if (g.ring) { tl[0][g.hs] = hu; tl[1][g.hs] = hk; }
+        Pair<T> *tl = tile[buf];
+        tl[g.so] = Pair<T>{c.u, c.k};
+        if (g.ring) tl[g.hs] = Pair<T>{hu, hk};
         const int x1 = (x + 1 == a.X) ? 0 : x + 1;
         const uint32_t n2 = stage_up(a, g, n1, x1);
         q.u = u[n2]; q.k = kc[n2];
@@ -206,8 +310,9 @@ __global__ void __launch_bounds__(TZ *TY) fk_step_v3(const StepArgs<T> a, const 
         const T react = a.rho * c.u * (T(1) - c.u);
         __syncthreads();
         const int o = g.so;
-        sp += a.cy * (relu(tl[1][o - RS] + c.k) * (tl[0][o - RS] - c.u) - relu(c.k + tl[1][o + RS]) * (c.u - tl[0][o + RS]));
-        sp += a.cz * (relu(tl[1][o - 1] + c.k) * (tl[0][o - 1] - c.u) - relu(c.k + tl[1][o + 1]) * (c.u - tl[0][o + 1]));
+        const Pair<T> ym = tl[o - RS], yp = tl[o + RS], zm = tl[o - 1], zp = tl[o + 1];
+        sp += a.cy * (relu(ym.b + c.k) * (ym.a - c.u) - relu(c.k + yp.b) * (c.u - yp.a));
+        sp += a.cz * (relu(zm.b + c.k) * (zm.a - c.u) - relu(c.k + zp.b) * (c.u - zp.a));
         const T un = c.u + a.dt * (sp + react);
         if (g.valid) {
             out[g.c] = un;
