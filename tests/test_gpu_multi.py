@@ -1,0 +1,42 @@
+"""Multi-GPU paths through torchrun (skipped on a one-GPU box): slab decomposition over NCCL must
+reproduce the undecomposed loop bitwise; the ensemble shards must cover every patient."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpus():
+    from tumorgrowthtoolkit_b200 import _native
+    import __graft_entry__ as ge
+    ge.build()
+    return _native.device_count()
+
+
+def _torchrun(n, script, *args, port=29561):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tools", script), *args]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+
+
+@pytest.mark.parametrize("model", ["dti", "fk2c"])
+def test_slab_over_nccl_is_bitwise(model):
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = _torchrun(2, "run_slab.py", "--model", model, "--steps", "13", "--halo", "3", "--factor", "0.5", "--check")
+    assert r["n_gpus"] == 2 and r["max_abs_diff_vs_undecomposed"] == 0.0
+    assert r["volume_rel_diff"] <= 1e-12
+
+
+def test_ensemble_two_ranks():
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = _torchrun(2, "run_ensemble.py", "--patients", "6", "--lowres", port=29562)
+    assert r["n_gpus"] == 2 and r["patients"] == 6 and r["glups"] > 0

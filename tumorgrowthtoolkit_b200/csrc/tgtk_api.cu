@@ -67,6 +67,8 @@ struct tgtk_sim {
     int force_tz = 0;      // 0: pick the tile width by lane waste
     bool use_graph = true;
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // by parity of the first step
+    cudaGraphExec_t slab_graph[2] = {nullptr, nullptr};   // tgtk_sim_run_slab: one block, by parity
+    void *slab_key_comm = nullptr; int slab_key_halo = 0, slab_key_owned = 0; double *slab_key_vol = nullptr;
     bool host_sched = false;   // no stop criterion: parity baked into launches (see StepArgs)
     int sum_x0 = 0, sum_x1 = -1;     // planes counted in the volume (-1: all)
     int cur_par = 0, cur_slot = 0;   // launch-time values of StepArgs::par / slot
@@ -348,6 +350,8 @@ static void drop_graph(tgtk_sim *s)
     for (int i = 0; i < 2; ++i) {
         if (s->graph_exec[i]) cudaGraphExecDestroy(s->graph_exec[i]);
         s->graph_exec[i] = nullptr;
+        if (s->slab_graph[i]) cudaGraphExecDestroy(s->slab_graph[i]);
+        s->slab_graph[i] = nullptr;
     }
 }
 
