@@ -16,7 +16,7 @@ def _built():
 
 
 @settings(max_examples=30, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
-@given(shape=shapes, seed=st.integers(0, 2 ** 20), variant=st.sampled_from([1, 2, 3]),
+@given(shape=shapes, seed=st.integers(0, 2 ** 20), variant=st.sampled_from([1, 2, 3, 4]),
        h=st.tuples(st.floats(0.5, 2.0), st.floats(0.5, 2.0), st.floats(0.5, 2.0)), nsteps=st.integers(1, 6))
 def test_fk_and_fk2c_any_box(oracle, shape, seed, variant, h, nsteps):
     from tumorgrowthtoolkit_b200 import _native as nat

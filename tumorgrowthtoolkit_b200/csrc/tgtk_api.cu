@@ -63,6 +63,7 @@ struct tgtk_sim {
     bool prepared = false;
     int variant = 0;       // 0: auto (default), 1: baseline, 2: marching via L1, 3: marching via shared memory
     int lx = 1;            // planes per block of the marching kernels
+    int v4_threads = 128;  // fk2c_step_v4 block size: 128 (32x4 threads, 32x8 voxels) or 256 (32x8 threads, 32x16 voxels)
     int pf = 1;            // FK_2c staged kernel: prefetch distance in planes (1: two register sets, 4 blocks/SM; 2: three sets)
     int force_tz = 0;      // 0: pick the tile width by lane waste
     bool use_graph = true;
@@ -72,7 +73,7 @@ struct tgtk_sim {
     bool host_sched = false;   // no stop criterion: parity baked into launches (see StepArgs)
     int sum_x0 = 0, sum_x1 = -1;     // planes counted in the volume (-1: all)
     int cur_par = 0, cur_slot = 0;   // launch-time values of StepArgs::par / slot
-    int minb = 3;          // FK_2c staged kernel: resident blocks per SM the register budget targets
+    int minb = 0;          // FK_2c staged kernel: resident blocks per SM the register budget targets
     unsigned partials_cap = 0;
     std::vector<void *> snaps;     // one allocation per snapshot: nfields * n * elem
     std::vector<int> snap_steps;
@@ -259,13 +260,15 @@ template <typename T> static void fill_args(const tgtk_sim *s, StepArgs<T> &a)
     a.sum_x1 = (s->sum_x1 < 0) ? p.X : s->sum_x1;
 }
 
-// variant 0 = auto: the faster of the two marching families per model and dtype, as measured on
-// B200 at the atlas box: FK fp64 and FK_DTI fp32 through L1 (v2), the rest staged (v3)
+// variant 0 = auto: the fastest kernel family per model and dtype, as measured on B200 at the atlas
+// box: FK fp64 and FK_DTI fp32 through L1 (v2), FK fp32 and FK_DTI fp64 staged (v3),
+// FK_2c staged with two voxels per thread (v4)
 static int effective_variant(const tgtk_sim *s)
 {
     if (s->variant != 0) return s->variant;
     if (s->p.model == TGTK_MODEL_FK) return (s->p.dtype == TGTK_F64) ? 2 : 3;
     if (s->p.model == TGTK_MODEL_DTI) return (s->p.dtype == TGTK_F64) ? 3 : 2;
+    if (s->p.model == TGTK_MODEL_FK_2C) return 4;     // two voxels per thread
     return 3;
 }
 
@@ -273,7 +276,18 @@ template <typename T> static cudaError_t launch_step(tgtk_sim *s)
 {
     StepArgs<T> a;
     fill_args(s, a);
-    if (s->lx > 0 && effective_variant(s) == 3) {   // shared-memory staged marching kernels
+    if (s->lx > 0 && effective_variant(s) == 4 && s->p.model == TGTK_MODEL_FK_2C) {   // two voxels per thread
+        const int mb = s->minb ? s->minb : ((sizeof(T) == 8) ? 2 : 3);
+        if (s->block.y == 4) {
+            if (mb >= 3) fk2c_step_v4<T, 32, 4, 6><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+            else fk2c_step_v4<T, 32, 4, 4><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+        } else {
+            if (mb >= 3) fk2c_step_v4<T, 32, 8, 3><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+            else fk2c_step_v4<T, 32, 8, 2><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+        }
+        return cudaGetLastError();
+    }
+    if (s->lx > 0 && effective_variant(s) >= 3) {   // shared-memory staged marching kernels
         const bool wide = (s->block.x == 32);
         switch (s->p.model) {
         case TGTK_MODEL_FK:
@@ -287,7 +301,7 @@ template <typename T> static cudaError_t launch_step(tgtk_sim *s)
             } else if (s->minb == 4) {
                 if (wide) fk2c_step_v3<T, 32, 8, 4><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
                 else fk2c_step_v3<T, 16, 16, 4><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
-            } else if (s->minb == 3) {
+            } else if (s->minb == 3 || s->minb == 0) {
                 if (wide) fk2c_step_v3<T, 32, 8, 3><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
                 else fk2c_step_v3<T, 16, 16, 3><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
             } else {
@@ -339,7 +353,7 @@ template <typename T> static const void *v3_kernel(int model, bool wide, int min
     case TGTK_MODEL_FK_2C:
         if (minb == 14) return wide ? (const void *)fk2c_step_v3s<T, 32, 8, 4> : (const void *)fk2c_step_v3s<T, 16, 16, 4>;
         if (minb == 4) return wide ? (const void *)fk2c_step_v3<T, 32, 8, 4> : (const void *)fk2c_step_v3<T, 16, 16, 4>;
-        if (minb == 3) return wide ? (const void *)fk2c_step_v3<T, 32, 8, 3> : (const void *)fk2c_step_v3<T, 16, 16, 3>;
+        if (minb == 3 || minb == 0) return wide ? (const void *)fk2c_step_v3<T, 32, 8, 3> : (const void *)fk2c_step_v3<T, 16, 16, 3>;
         return wide ? (const void *)fk2c_step_v3<T, 32, 8> : (const void *)fk2c_step_v3<T, 16, 16>;
     default: return wide ? (const void *)dti_step_v3<T, 32, 8> : (const void *)dti_step_v3<T, 16, 16>;
     }
@@ -353,6 +367,17 @@ static void drop_graph(tgtk_sim *s)
         if (s->slab_graph[i]) cudaGraphExecDestroy(s->slab_graph[i]);
         s->slab_graph[i] = nullptr;
     }
+}
+
+static const void *v4_kernel(int dtype, int rows, int minb)
+{
+    if (minb == 0) minb = (dtype == TGTK_F64) ? 2 : 3;   // fp64: 120 registers, fp32: 76 (measured faster)
+    if (dtype == TGTK_F64) {
+        if (rows == 4) return minb >= 3 ? (const void *)fk2c_step_v4<double, 32, 4, 6> : (const void *)fk2c_step_v4<double, 32, 4, 4>;
+        return minb >= 3 ? (const void *)fk2c_step_v4<double, 32, 8, 3> : (const void *)fk2c_step_v4<double, 32, 8, 2>;
+    }
+    if (rows == 4) return minb >= 3 ? (const void *)fk2c_step_v4<float, 32, 4, 6> : (const void *)fk2c_step_v4<float, 32, 4, 4>;
+    return minb >= 3 ? (const void *)fk2c_step_v4<float, 32, 8, 3> : (const void *)fk2c_step_v4<float, 32, 8, 2>;
 }
 
 static bool has_v2(int model) { return model == TGTK_MODEL_FK || model == TGTK_MODEL_FK_2C || model == TGTK_MODEL_DTI; }
@@ -369,23 +394,27 @@ static int configure_launch(tgtk_sim *s)
         int best_tz = 32;
         double best = 1e30;
         for (int tz : {64, 32, 16}) {
-            if (variant == 3 && tz == 64) continue;   // staged kernels: 32x8 or 16x16 tiles
+            if (variant >= 3 && tz == 64) continue;   // staged kernels: 32x8 or 16x16 tiles
             if (s->force_tz && tz != s->force_tz) continue;
             const int ty = 256 / tz;
             const double padded = (double)((p.Z + tz - 1) / tz * tz) * ((p.Y + ty - 1) / ty * ty);
             const double cost = padded / ((double)p.Z * p.Y) + 0.08 * (tz == 16) + 0.03 * (tz == 64);   // full-warp rows measure faster
             if (cost < best) { best = cost; best_tz = tz; }
         }
-        const int tz = best_tz, ty = 256 / tz;
+        const bool two_rows = (variant == 4 && p.model == TGTK_MODEL_FK_2C);   // fk2c_step_v4: 32 x 16 voxel tile
+        const int v4rows = (s->v4_threads == 128) ? 4 : 8;                       // thread rows; voxel rows = 2x
+        const int tz = two_rows ? 32 : best_tz, ty = two_rows ? 2 * v4rows : 256 / tz;
         const int tiles = ((p.Z + tz - 1) / tz) * ((p.Y + ty - 1) / ty);
         // Segment length: trade the tail of the last wave (blocks / resident slots not an
         // integer) against the two extra planes every segment loads to prime its pipeline.
         int per_sm = 2, sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
-        const void *fn = (variant == 3)
+        const void *fn = two_rows ? v4_kernel(p.dtype, v4rows, s->minb)
+                         : (variant >= 3)
                              ? ((p.dtype == TGTK_F64) ? v3_kernel<double>(p.model, tz == 32, s->pf == 1 ? 14 : s->minb) : v3_kernel<float>(p.model, tz == 32, s->pf == 1 ? 14 : s->minb))
                              : ((p.dtype == TGTK_F64) ? v2_kernel<double>(p.model) : v2_kernel<float>(p.model));
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+        const int nthreads = two_rows ? 32 * v4rows : 256;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, nthreads, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
         const double slots = (double)sms * per_sm;
         int best_lx = p.X;
         double best_eff = -1.0;
@@ -397,7 +426,7 @@ static int configure_launch(tgtk_sim *s)
         }
         s->lx = best_lx;
         const int nseg = (p.X + s->lx - 1) / s->lx;
-        s->block = dim3(tz, ty, 1);
+        s->block = dim3(tz, two_rows ? v4rows : ty, 1);
         s->grid = dim3((p.Z + tz - 1) / tz, (p.Y + ty - 1) / ty, nseg);
     } else {
         s->lx = 0;
@@ -615,6 +644,7 @@ int tgtk_sim_create(tgtk_sim **out, const tgtk_params *params, int device, void 
     if (const char *v = getenv("TGTK_VARIANT")) s->variant = atoi(v);
     if (const char *v = getenv("TGTK_MINB")) s->minb = atoi(v);
     if (const char *v = getenv("TGTK_PF")) s->pf = atoi(v);
+    if (const char *v = getenv("TGTK_V4_THREADS")) s->v4_threads = atoi(v);
     if (const char *v = getenv("TGTK_GRAPH")) s->use_graph = atoi(v) != 0;
     if (const char *v = getenv("TGTK_TZ")) s->force_tz = atoi(v);
     *out = s;  // from here on tgtk_sim_destroy cleans up on failure
@@ -673,7 +703,7 @@ void tgtk_sim_destroy(tgtk_sim *s)
 int tgtk_sim_set_variant(tgtk_sim *s, int variant)
 {
     if (!s) return fail("tgtk_sim_set_variant", "null argument");
-    if (variant < 0 || variant > 3) return fail("tgtk_sim_set_variant", "variant must be 0 (auto), 1, 2 or 3");
+    if (variant < 0 || variant > 4) return fail("tgtk_sim_set_variant", "variant must be 0 (auto) or 1..4");
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(s->stream));
     s->variant = variant;

@@ -271,6 +271,161 @@ __global__ void __launch_bounds__(TZ *TY, MINB) fk2c_step_v3s(const StepArgs<T> 
     step_end<T, 2>(a, sc, sP, sN);
 }
 
+// ---- FK_2c, two voxels per thread -------------------------------------------------------------------
+// Same staging as fk2c_step_v3s, but a thread owns two rows (y, y+1) of its column tile: the face
+// between them is evaluated once and needs no shared-memory read, the tile is 32 x 16 voxels for the
+// same 256 threads (ring 96 elements per 512 voxels instead of 80 per 256), and loop / address /
+// barrier overhead is paid once per two voxels.  The two voxels give each warp two independent
+// instruction streams, which replaces the occupancy the doubled register state costs.
+struct Stage2 {
+    int x0, x1;
+    bool valid0, valid1, ring;
+    uint32_t c0, c1, prev0, prev1, h;
+    uint32_t sx, wrap_back;
+    int so, hs;          // shared-memory slot of the upper-row voxel (the lower one is so + RS) / ring slot
+};
+
+template <typename T, int TZ, int TYT, int RS>
+__device__ __forceinline__ Stage2 stage2_setup(const StepArgs<T> &a, int lx)
+{
+    constexpr int TYV = 2 * TYT;          // voxel rows per tile
+    Stage2 g;
+    const int tz = threadIdx.x, ty = threadIdx.y, tid = ty * TZ + tz;
+    const int z0 = blockIdx.x * TZ, y0 = blockIdx.y * TYV;
+    const int r0 = y0 + 2 * ty;
+    g.valid0 = (z0 + tz < a.Z) && (r0 < a.Y);
+    g.valid1 = (z0 + tz < a.Z) && (r0 + 1 < a.Y);
+    g.x0 = blockIdx.z * lx;
+    g.x1 = min(g.x0 + lx, a.X);
+    g.sx = (uint32_t)a.sx;
+    g.wrap_back = (uint32_t)(a.X - 1) * g.sx;
+    const uint32_t sy = (uint32_t)a.sy, base = (uint32_t)g.x0 * g.sx;
+    const uint32_t zc = (uint32_t)wrap_coord(z0 + tz, a.Z);
+    g.c0 = base + (uint32_t)wrap_coord(r0, a.Y) * sy + zc;
+    g.c1 = base + (uint32_t)wrap_coord(r0 + 1, a.Y) * sy + zc;
+    g.prev0 = (g.x0 == 0) ? g.c0 + g.wrap_back : g.c0 - g.sx;
+    g.prev1 = (g.x0 == 0) ? g.c1 + g.wrap_back : g.c1 - g.sx;
+    g.so = (2 * ty + 1) * RS + tz + 1;
+    int hr = 1, hc = 1;
+    g.ring = tid < 2 * TZ + 2 * TYV;
+    if (tid < TZ) { hr = 0; hc = tid + 1; }
+    else if (tid < 2 * TZ) { hr = TYV + 1; hc = tid - TZ + 1; }
+    else if (tid < 2 * TZ + TYV) { hr = tid - 2 * TZ + 1; hc = 0; }
+    else if (g.ring) { hr = tid - 2 * TZ - TYV + 1; hc = TZ + 1; }
+    g.hs = hr * RS + hc;
+    g.h = base + (uint32_t)wrap_coord(y0 - 1 + hr, a.Y) * sy + (uint32_t)wrap_coord(z0 - 1 + hc, a.Z);
+    return g;
+}
+
+template <typename T> struct Vox2c { T p, n, s, b, k; };
+
+template <typename T, int TZ, int TYT, int MINB = 2>
+__global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> a, const int lx)
+{
+    constexpr int TYV = 2 * TYT, RS = TZ + 2, PL = (TYV + 2) * RS;
+    __shared__ Pair<T> tile[2][2][PL];     // [buffer][(P, k_eff), (S, b)][slot]
+    const StepCtl sc = step_begin(a);
+    if (sc.stop) return;
+    const T *__restrict__ P = a.buf[sc.par][0];
+    const T *__restrict__ N = a.buf[sc.par][1];
+    const T *__restrict__ S = a.buf[sc.par][2];
+    T *__restrict__ Po = a.buf[sc.par ^ 1][0];
+    T *__restrict__ No = a.buf[sc.par ^ 1][1];
+    T *__restrict__ So = a.buf[sc.par ^ 1][2];
+    const T *__restrict__ kc = a.coef[0];
+    const T *__restrict__ bc = a.coef[1];
+    Stage2 g = stage2_setup<T, TZ, TYT, RS>(a, lx);
+    const T closed = -Big<T>::v;
+    auto keff = [&](T pq, T nq, T kq) { return (pq + nq <= a.th_necro) ? kq : closed; };
+    auto load = [&](Vox2c<T> &v, uint32_t off) { v.p = P[off]; v.n = N[off]; v.s = S[off]; v.b = bc[off]; v.k = kc[off]; };
+    double sP = 0.0, sN = 0.0;
+
+    Vox2c<T> A0, A1, B0, B1;               // rows (y, y+1) of plane x (A) and plane x+1 (B); roles swap
+    load(A0, g.c0); A0.k = keff(A0.p, A0.n, A0.k);
+    load(A1, g.c1); A1.k = keff(A1.p, A1.n, A1.k);
+    T fp_lo0, fs_lo0, fp_lo1, fs_lo1;      // fluxes through the faces below (x-1 | x)
+    {
+        const T pm0 = P[g.prev0], pm1 = P[g.prev1];
+        fp_lo0 = relu(keff(pm0, N[g.prev0], kc[g.prev0]) + A0.k) * (pm0 - A0.p);
+        fs_lo0 = relu(bc[g.prev0] + A0.b) * (S[g.prev0] - A0.s);
+        fp_lo1 = relu(keff(pm1, N[g.prev1], kc[g.prev1]) + A1.k) * (pm1 - A1.p);
+        fs_lo1 = relu(bc[g.prev1] + A1.b) * (S[g.prev1] - A1.s);
+    }
+    T hp = 0, hn = 0, hk = 0, hsv = 0, hb = 0;
+    if (g.ring) { hp = P[g.h]; hn = N[g.h]; hk = kc[g.h]; hsv = S[g.h]; hb = bc[g.h]; }
+    int buf = 0;
+
+    auto step = [&](int x, const Vox2c<T> &c0, const Vox2c<T> &c1, Vox2c<T> &p0, Vox2c<T> &p1) {
+        Pair<T>(*tl)[PL] = tile[buf];
+        const int o0 = g.so, o1 = g.so + RS;
+        tl[0][o0] = Pair<T>{c0.p, c0.k};
+        tl[1][o0] = Pair<T>{c0.s, c0.b};
+        tl[0][o1] = Pair<T>{c1.p, c1.k};
+        tl[1][o1] = Pair<T>{c1.s, c1.b};
+        if (g.ring) {
+            tl[0][g.hs] = Pair<T>{hp, keff(hp, hn, hk)};
+            tl[1][g.hs] = Pair<T>{hsv, hb};
+        }
+        // request plane x+1: both own voxels and the ring
+        const uint32_t n0 = (x + 1 == a.X) ? g.c0 - g.wrap_back : g.c0 + g.sx;
+        const uint32_t n1 = (x + 1 == a.X) ? g.c1 - g.wrap_back : g.c1 + g.sx;
+        load(p0, n0);
+        load(p1, n1);
+        g.h = (x + 1 == a.X) ? g.h - g.wrap_back : g.h + g.sx;
+        if (g.ring) { hp = P[g.h]; hn = N[g.h]; hk = kc[g.h]; hsv = S[g.h]; hb = bc[g.h]; }
+        // work that needs neither neighbours nor plane x+1
+        const T H0 = heaviside50_fast(c0.s, a.sigma_np), H1 = heaviside50_fast(c1.s, a.sigma_np);
+        const T react0 = a.rho * (c0.s * c0.p) * ((T(1) - c0.p) - c0.n) - (a.lambda_np * c0.p) * H0;
+        const T react1 = a.rho * (c1.s * c1.p) * ((T(1) - c1.p) - c1.n) - (a.lambda_np * c1.p) * H1;
+        // the face between the two own rows: no shared memory involved
+        const T fp_mid = relu(c0.k + c1.k) * (c0.p - c1.p);
+        const T fs_mid = relu(c0.b + c1.b) * (c0.s - c1.s);
+        __syncthreads();
+        const Pair<T> pu = tl[0][o0 - RS], pd = tl[0][o1 + RS];                       // rows y-1 and y+2: (P, k)
+        const Pair<T> su = tl[1][o0 - RS], sd = tl[1][o1 + RS];                       // (S, b)
+        const Pair<T> pl0 = tl[0][o0 - 1], pr0 = tl[0][o0 + 1], pl1 = tl[0][o1 - 1], pr1 = tl[0][o1 + 1];
+        const Pair<T> sl0 = tl[1][o0 - 1], sr0 = tl[1][o0 + 1], sl1 = tl[1][o1 - 1], sr1 = tl[1][o1 + 1];
+        T sp0 = a.cy * (relu(pu.b + c0.k) * (pu.a - c0.p) - fp_mid);
+        T sp1 = a.cy * (fp_mid - relu(c1.k + pd.b) * (c1.p - pd.a));
+        T ss0 = a.ey * (relu(su.b + c0.b) * (su.a - c0.s) - fs_mid);
+        T ss1 = a.ey * (fs_mid - relu(c1.b + sd.b) * (c1.s - sd.a));
+        sp0 += a.cz * (relu(pl0.b + c0.k) * (pl0.a - c0.p) - relu(c0.k + pr0.b) * (c0.p - pr0.a));
+        sp1 += a.cz * (relu(pl1.b + c1.k) * (pl1.a - c1.p) - relu(c1.k + pr1.b) * (c1.p - pr1.a));
+        ss0 += a.ez * (relu(sl0.b + c0.b) * (sl0.a - c0.s) - relu(c0.b + sr0.b) * (c0.s - sr0.a));
+        ss1 += a.ez * (relu(sl1.b + c1.b) * (sl1.a - c1.s) - relu(c1.b + sr1.b) * (c1.s - sr1.a));
+        // x faces last: plane x+1 has had the whole step to arrive
+        p0.k = keff(p0.p, p0.n, p0.k);
+        p1.k = keff(p1.p, p1.n, p1.k);
+        const T fp_hi0 = relu(c0.k + p0.k) * (c0.p - p0.p), fs_hi0 = relu(c0.b + p0.b) * (c0.s - p0.s);
+        const T fp_hi1 = relu(c1.k + p1.k) * (c1.p - p1.p), fs_hi1 = relu(c1.b + p1.b) * (c1.s - p1.s);
+        sp0 += a.cx * (fp_lo0 - fp_hi0);
+        sp1 += a.cx * (fp_lo1 - fp_hi1);
+        ss0 += a.ex * (fs_lo0 - fs_hi0);
+        ss1 += a.ex * (fs_lo1 - fs_hi1);
+        const T pn0 = c0.p + a.dt * (sp0 + react0), pn1 = c1.p + a.dt * (sp1 + react1);
+        const T nn0 = c0.n + a.dt * ((a.lambda_np * pn0) * H0), nn1 = c1.n + a.dt * ((a.lambda_np * pn1) * H1);
+        const T sn0 = c0.s + a.dt * (ss0 - (a.lambda_s * c0.s) * pn0), sn1 = c1.s + a.dt * (ss1 - (a.lambda_s * c1.s) * pn1);
+        const bool cnt = counts(a, x);
+        if (g.valid0) {
+            Po[g.c0] = pn0; No[g.c0] = nn0; So[g.c0] = sn0;
+            if (cnt) { sP += (double)pn0; sN += (double)nn0; }
+        }
+        if (g.valid1) {
+            Po[g.c1] = pn1; No[g.c1] = nn1; So[g.c1] = sn1;
+            if (cnt) { sP += (double)pn1; sN += (double)nn1; }
+        }
+        fp_lo0 = fp_hi0; fs_lo0 = fs_hi0; fp_lo1 = fp_hi1; fs_lo1 = fs_hi1;
+        g.c0 = n0; g.c1 = n1;
+        buf ^= 1;
+    };
+    for (int x = g.x0; x < g.x1; x += 2) {
+        step(x, A0, A1, B0, B1);
+        if (x + 1 >= g.x1) break;
+        step(x + 1, B0, B1, A0, A1);
+    }
+    step_end<T, 2>(a, sc, sP, sN);
+}
+
 // ---- FK --------------------------------------------------------------------------------------------
 template <typename T> struct ColFkS { T u, k; };
 
