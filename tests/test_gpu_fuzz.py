@@ -58,7 +58,7 @@ def test_fk_and_fk2c_any_box(oracle, shape, seed, variant, h, nsteps):
 
 
 @settings(max_examples=15, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
-@given(shape=shapes, seed=st.integers(0, 2 ** 20), variant=st.sampled_from([1, 2, 3]), nsteps=st.integers(1, 5))
+@given(shape=shapes, seed=st.integers(0, 2 ** 20), variant=st.sampled_from([1, 2, 3, 4]), nsteps=st.integers(1, 5))
 def test_dti_any_box_bitwise(oracle, shape, seed, variant, nsteps):
     from tumorgrowthtoolkit_b200 import _native as nat
     rng = np.random.default_rng(seed)

@@ -260,22 +260,28 @@ template <typename T> static void fill_args(const tgtk_sim *s, StepArgs<T> &a)
     a.sum_x1 = (s->sum_x1 < 0) ? p.X : s->sum_x1;
 }
 
-// variant 0 = auto: the fastest kernel family per model and dtype, as measured on B200 at the atlas
-// box: FK fp64 and FK_DTI fp32 through L1 (v2), FK fp32 and FK_DTI fp64 staged (v3),
-// FK_2c staged with two voxels per thread (v4)
+// variant 0 = auto = the staged kernels with two voxels per thread (v4), fastest for every model and
+// dtype measured on B200; 1, 2, 3 select the earlier families (cross-checks)
 static int effective_variant(const tgtk_sim *s)
 {
     if (s->variant != 0) return s->variant;
-    if (s->p.model == TGTK_MODEL_FK) return (s->p.dtype == TGTK_F64) ? 2 : 3;
-    if (s->p.model == TGTK_MODEL_DTI) return (s->p.dtype == TGTK_F64) ? 3 : 2;
-    if (s->p.model == TGTK_MODEL_FK_2C) return 4;     // two voxels per thread
-    return 3;
+    return 4;
 }
 
 template <typename T> static cudaError_t launch_step(tgtk_sim *s)
 {
     StepArgs<T> a;
     fill_args(s, a);
+    if (s->lx > 0 && effective_variant(s) == 4 && s->p.model == TGTK_MODEL_FK) {
+        if (s->block.y == 4) fk_step_v4<T, 32, 4, 8><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+        else fk_step_v4<T, 32, 8, 4><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+        return cudaGetLastError();
+    }
+    if (s->lx > 0 && effective_variant(s) == 4 && s->p.model == TGTK_MODEL_DTI) {
+        if (s->block.y == 4) dti_step_v4<T, 32, 4, 8><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+        else dti_step_v4<T, 32, 8, 4><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+        return cudaGetLastError();
+    }
     if (s->lx > 0 && effective_variant(s) == 4 && s->p.model == TGTK_MODEL_FK_2C) {   // two voxels per thread
         const int mb = s->minb ? s->minb : ((sizeof(T) == 8) ? 2 : 3);
         if (s->block.y == 4) {
@@ -369,8 +375,16 @@ static void drop_graph(tgtk_sim *s)
     }
 }
 
-static const void *v4_kernel(int dtype, int rows, int minb)
+static const void *v4_kernel(int model, int dtype, int rows, int minb)
 {
+    if (model == TGTK_MODEL_FK) {
+        if (dtype == TGTK_F64) return rows == 4 ? (const void *)fk_step_v4<double, 32, 4, 8> : (const void *)fk_step_v4<double, 32, 8, 4>;
+        return rows == 4 ? (const void *)fk_step_v4<float, 32, 4, 8> : (const void *)fk_step_v4<float, 32, 8, 4>;
+    }
+    if (model == TGTK_MODEL_DTI) {
+        if (dtype == TGTK_F64) return rows == 4 ? (const void *)dti_step_v4<double, 32, 4, 8> : (const void *)dti_step_v4<double, 32, 8, 4>;
+        return rows == 4 ? (const void *)dti_step_v4<float, 32, 4, 8> : (const void *)dti_step_v4<float, 32, 8, 4>;
+    }
     if (minb == 0) minb = (dtype == TGTK_F64) ? 2 : 3;   // fp64: 120 registers, fp32: 76 (measured faster)
     if (dtype == TGTK_F64) {
         if (rows == 4) return minb >= 3 ? (const void *)fk2c_step_v4<double, 32, 4, 6> : (const void *)fk2c_step_v4<double, 32, 4, 4>;
@@ -401,7 +415,7 @@ static int configure_launch(tgtk_sim *s)
             const double cost = padded / ((double)p.Z * p.Y) + 0.08 * (tz == 16) + 0.03 * (tz == 64);   // full-warp rows measure faster
             if (cost < best) { best = cost; best_tz = tz; }
         }
-        const bool two_rows = (variant == 4 && p.model == TGTK_MODEL_FK_2C);   // fk2c_step_v4: 32 x 16 voxel tile
+        const bool two_rows = (variant == 4);   // *_step_v4: 32 x 8 or 32 x 16 voxel tile, two rows per thread
         const int v4rows = (s->v4_threads == 128) ? 4 : 8;                       // thread rows; voxel rows = 2x
         const int tz = two_rows ? 32 : best_tz, ty = two_rows ? 2 * v4rows : 256 / tz;
         const int tiles = ((p.Z + tz - 1) / tz) * ((p.Y + ty - 1) / ty);
@@ -409,7 +423,7 @@ static int configure_launch(tgtk_sim *s)
         // integer) against the two extra planes every segment loads to prime its pipeline.
         int per_sm = 2, sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
-        const void *fn = two_rows ? v4_kernel(p.dtype, v4rows, s->minb)
+        const void *fn = two_rows ? v4_kernel(p.model, p.dtype, v4rows, s->minb)
                          : (variant >= 3)
                              ? ((p.dtype == TGTK_F64) ? v3_kernel<double>(p.model, tz == 32, s->pf == 1 ? 14 : s->minb) : v3_kernel<float>(p.model, tz == 32, s->pf == 1 ? 14 : s->minb))
                              : ((p.dtype == TGTK_F64) ? v2_kernel<double>(p.model) : v2_kernel<float>(p.model));

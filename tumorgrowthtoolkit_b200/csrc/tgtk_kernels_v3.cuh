@@ -426,6 +426,137 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> 
     step_end<T, 2>(a, sc, sP, sN);
 }
 
+// ---- FK, two voxels per thread (see fk2c_step_v4) -------------------------------------------------
+template <typename T> struct VoxFk { T u, k; };
+
+template <typename T, int TZ, int TYT, int MINB = 4>
+__global__ void __launch_bounds__(TZ *TYT, MINB) fk_step_v4(const StepArgs<T> a, const int lx)
+{
+    constexpr int TYV = 2 * TYT, RS = TZ + 2, PL = (TYV + 2) * RS;
+    __shared__ Pair<T> tile[2][PL];        // [buffer][slot] of (u, k)
+    const StepCtl sc = step_begin(a);
+    if (sc.stop) return;
+    const T *__restrict__ u = a.buf[sc.par][0];
+    T *__restrict__ out = a.buf[sc.par ^ 1][0];
+    const T *__restrict__ kc = a.coef[0];
+    Stage2 g = stage2_setup<T, TZ, TYT, RS>(a, lx);
+    double s = 0.0;
+
+    VoxFk<T> A0, A1, B0, B1;
+    A0.u = u[g.c0]; A0.k = kc[g.c0];
+    A1.u = u[g.c1]; A1.k = kc[g.c1];
+    T f_lo0 = relu(kc[g.prev0] + A0.k) * (u[g.prev0] - A0.u);
+    T f_lo1 = relu(kc[g.prev1] + A1.k) * (u[g.prev1] - A1.u);
+    T hu = 0, hk = 0;
+    if (g.ring) { hu = u[g.h]; hk = kc[g.h]; }
+    int buf = 0;
+
+    auto step = [&](int x, const VoxFk<T> &c0, const VoxFk<T> &c1, VoxFk<T> &p0, VoxFk<T> &p1) {
+        Pair<T> *tl = tile[buf];
+        const int o0 = g.so, o1 = g.so + RS;
+        tl[o0] = Pair<T>{c0.u, c0.k};
+        tl[o1] = Pair<T>{c1.u, c1.k};
+        if (g.ring) tl[g.hs] = Pair<T>{hu, hk};
+        const uint32_t n0 = (x + 1 == a.X) ? g.c0 - g.wrap_back : g.c0 + g.sx;
+        const uint32_t n1 = (x + 1 == a.X) ? g.c1 - g.wrap_back : g.c1 + g.sx;
+        p0.u = u[n0]; p0.k = kc[n0];
+        p1.u = u[n1]; p1.k = kc[n1];
+        g.h = (x + 1 == a.X) ? g.h - g.wrap_back : g.h + g.sx;
+        if (g.ring) { hu = u[g.h]; hk = kc[g.h]; }
+        const T react0 = a.rho * c0.u * (T(1) - c0.u), react1 = a.rho * c1.u * (T(1) - c1.u);
+        const T f_mid = relu(c0.k + c1.k) * (c0.u - c1.u);
+        __syncthreads();
+        const Pair<T> up = tl[o0 - RS], dn = tl[o1 + RS];
+        const Pair<T> l0 = tl[o0 - 1], r0 = tl[o0 + 1], l1 = tl[o1 - 1], r1 = tl[o1 + 1];
+        T sp0 = a.cy * (relu(up.b + c0.k) * (up.a - c0.u) - f_mid);
+        T sp1 = a.cy * (f_mid - relu(c1.k + dn.b) * (c1.u - dn.a));
+        sp0 += a.cz * (relu(l0.b + c0.k) * (l0.a - c0.u) - relu(c0.k + r0.b) * (c0.u - r0.a));
+        sp1 += a.cz * (relu(l1.b + c1.k) * (l1.a - c1.u) - relu(c1.k + r1.b) * (c1.u - r1.a));
+        const T f_hi0 = relu(c0.k + p0.k) * (c0.u - p0.u), f_hi1 = relu(c1.k + p1.k) * (c1.u - p1.u);
+        sp0 += a.cx * (f_lo0 - f_hi0);
+        sp1 += a.cx * (f_lo1 - f_hi1);
+        const T un0 = c0.u + a.dt * (sp0 + react0), un1 = c1.u + a.dt * (sp1 + react1);
+        const bool cnt = counts(a, x);
+        if (g.valid0) { out[g.c0] = un0; if (cnt) s += (double)un0; }
+        if (g.valid1) { out[g.c1] = un1; if (cnt) s += (double)un1; }
+        f_lo0 = f_hi0; f_lo1 = f_hi1;
+        g.c0 = n0; g.c1 = n1;
+        buf ^= 1;
+    };
+    for (int x = g.x0; x < g.x1; x += 2) {
+        step(x, A0, A1, B0, B1);
+        if (x + 1 >= g.x1) break;
+        step(x + 1, B0, B1, A0, A1);
+    }
+    step_end<T, 1>(a, sc, s, 0.0);
+}
+
+// ---- FK_DTI, two voxels per thread (reference rounding order, bitwise equal to dti_step_v3) ----------
+template <typename T> struct VoxDti { T u, d0, d1, d2; };
+
+template <typename T, int TZ, int TYT, int MINB = 4>
+__global__ void __launch_bounds__(TZ *TYT, MINB) dti_step_v4(const StepArgs<T> a, const int lx)
+{
+    using R = Rn<T>;
+    constexpr int TYV = 2 * TYT, RS = TZ + 2, PL = (TYV + 2) * RS;
+    __shared__ T tile[2][PL];
+    const StepCtl sc = step_begin(a);
+    if (sc.stop) return;
+    const T *__restrict__ u = a.buf[sc.par][0];
+    T *__restrict__ out = a.buf[sc.par ^ 1][0];
+    const T *__restrict__ dxa = a.coef[0];
+    const T *__restrict__ dya = a.coef[1];
+    const T *__restrict__ dza = a.coef[2];
+    Stage2 g = stage2_setup<T, TZ, TYT, RS>(a, lx);
+    double s = 0.0;
+    auto load = [&](VoxDti<T> &v, uint32_t off) { v.u = u[off]; v.d0 = dxa[off]; v.d1 = dya[off]; v.d2 = dza[off]; };
+
+    VoxDti<T> A0, A1, B0, B1;
+    load(A0, g.c0);
+    load(A1, g.c1);
+    T um0 = u[g.prev0], um1 = u[g.prev1];
+    T hu = 0;
+    if (g.ring) hu = u[g.h];
+    int buf = 0;
+
+    auto one = [&](const VoxDti<T> &c, T um, T up, T uym, T uyp, T uzm, T uzp) {
+        const T sx = R::mul(a.cx, R::sub(R::mul(c.d0, R::sub(um, c.u)), R::mul(c.d0, R::sub(c.u, up))));
+        const T sy = R::mul(a.cy, R::sub(R::mul(c.d1, R::sub(uym, c.u)), R::mul(c.d1, R::sub(c.u, uyp))));
+        const T sz = R::mul(a.cz, R::sub(R::mul(c.d2, R::sub(uzm, c.u)), R::mul(c.d2, R::sub(c.u, uzp))));
+        const T sp = R::add(R::add(sx, sy), sz);
+        const T react = R::mul(a.rho, R::mul(c.u, R::sub(T(1), c.u)));
+        return R::add(c.u, R::mul(R::add(sp, react), a.dt));
+    };
+    auto step = [&](int x, const VoxDti<T> &c0, const VoxDti<T> &c1, VoxDti<T> &p0, VoxDti<T> &p1) {
+        T *tl = tile[buf];
+        const int o0 = g.so, o1 = g.so + RS;
+        tl[o0] = c0.u;
+        tl[o1] = c1.u;
+        if (g.ring) tl[g.hs] = hu;
+        const uint32_t n0 = (x + 1 == a.X) ? g.c0 - g.wrap_back : g.c0 + g.sx;
+        const uint32_t n1 = (x + 1 == a.X) ? g.c1 - g.wrap_back : g.c1 + g.sx;
+        load(p0, n0);
+        load(p1, n1);
+        g.h = (x + 1 == a.X) ? g.h - g.wrap_back : g.h + g.sx;
+        if (g.ring) hu = u[g.h];
+        __syncthreads();
+        const T un0 = one(c0, um0, p0.u, tl[o0 - RS], c1.u, tl[o0 - 1], tl[o0 + 1]);
+        const T un1 = one(c1, um1, p1.u, c0.u, tl[o1 + RS], tl[o1 - 1], tl[o1 + 1]);
+        const bool cnt = counts(a, x);
+        if (g.valid0) { out[g.c0] = un0; if (cnt) s += (double)un0; }
+        if (g.valid1) { out[g.c1] = un1; if (cnt) s += (double)un1; }
+        um0 = c0.u; um1 = c1.u;
+        g.c0 = n0; g.c1 = n1;
+        buf ^= 1;
+    };
+    for (int x = g.x0; x < g.x1; x += 2) {
+        step(x, A0, A1, B0, B1);
+        if (x + 1 >= g.x1) break;
+        step(x + 1, B0, B1, A0, A1);
+    }
+    step_end<T, 1>(a, sc, s, 0.0);
+}
+
 // ---- FK --------------------------------------------------------------------------------------------
 template <typename T> struct ColFkS { T u, k; };
 
