@@ -111,6 +111,10 @@ int tgtk_device_count(int *count);
  * library creates its own non-blocking stream).  Replaces the array set-up part of
  * Solver.solve() after cropping (FK/FK.py:197-208). */
 int tgtk_sim_create(tgtk_sim **out, const tgtk_params *params, int device, void *stream);
+/* flags: TGTK_CREATE_IPC allocates the state buffers so that they can be shared with the
+ * neighbouring ranks' processes (tgtk_sim_ipc_export / tgtk_sim_ipc_connect). */
+#define TGTK_CREATE_IPC 1
+int tgtk_sim_create_ex(tgtk_sim **out, const tgtk_params *params, int device, void *stream, int flags);
 void tgtk_sim_destroy(tgtk_sim *sim);
 
 /* Kernel family: 0 (default) = auto, 3 = marching kernels staged through shared memory,
@@ -139,6 +143,23 @@ int tgtk_nccl_unique_id(char id[128]);
 int tgtk_nccl_comm_create(void **comm, const char id[128], int rank, int world, int device);
 void tgtk_nccl_comm_destroy(void *comm);
 int tgtk_sim_run_slab(tgtk_sim *sim, void *comm, int nsteps, int halo, int owned, int prev, int next);
+
+/* Peer-to-peer slab driver: no NCCL.  Each rank maps its neighbours' state buffers and a few flag
+ * words (CUDA IPC, NVLink / NVSwitch peer access) and, after every block of `halo` steps, PUSHES
+ * its owned boundary planes straight into the neighbours' ghost planes with peer copies, fenced
+ * by two tiny signal-and-wait kernels (epoch counters in peer memory: "my block is done, you may
+ * overwrite my ghosts" / "your ghosts are filled").  The whole block is replayed from a CUDA graph.
+ *   tgtk_sim_ipc_export : TGTK_IPC_BYTES bytes describing this rank's buffers (send to neighbours)
+ *   tgtk_sim_ipc_connect: map the previous / next rank's buffers (same_peer: world == 2, both
+ *                          neighbours are one process; NULL handles: world == 1)
+ * The simulation must have been created with TGTK_CREATE_IPC.  Spin-waits are bounded (about two
+ * seconds); a time-out sets an error that tgtk_sim_sync reports. */
+#define TGTK_IPC_BYTES (7 * 64)
+int tgtk_sim_ipc_export(tgtk_sim *sim, unsigned char *out);
+int tgtk_sim_ipc_connect(tgtk_sim *sim, const unsigned char *prev, const unsigned char *next, int same_peer);
+int tgtk_sim_run_slab_p2p(tgtk_sim *sim, int nsteps, int halo, int owned);
+/* 0, or which handshake of the peer-to-peer driver timed out (1: block done, 2: ghosts pushed). */
+int tgtk_sim_slab_error(tgtk_sim *sim, int *err);
 
 /* Host -> device.  `host` is float64 with element strides (sx,sy,sz); any strides are
  * accepted (rows with sz==1 are copied directly, otherwise gathered on the host).  If

@@ -26,11 +26,13 @@ def _torchrun(n, script, *args, port=29561):
     return json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
 
 
+@pytest.mark.parametrize("driver", ["p2p", "native", "torch"])
 @pytest.mark.parametrize("model", ["dti", "fk2c"])
-def test_slab_over_nccl_is_bitwise(model):
+def test_slab_two_ranks_is_bitwise(model, driver):
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")
-    r = _torchrun(2, "run_slab.py", "--model", model, "--steps", "13", "--halo", "3", "--factor", "0.5", "--check")
+    r = _torchrun(2, "run_slab.py", "--model", model, "--steps", "13", "--halo", "3", "--factor", "0.5", "--check",
+                  "--driver", driver)
     assert r["n_gpus"] == 2 and r["max_abs_diff_vs_undecomposed"] == 0.0
     assert r["volume_rel_diff"] <= 1e-12
 

@@ -312,9 +312,9 @@ def test_slab_single_rank_equals_plain_loop(L):
     u0 = rng.uniform(0, 0.5, shape)
     args = (u0, wm, gm, 0.1, 1.0, 10.0, 0.3, 0.02, 1.0, 1.1, 0.9, 11)
     ref = _loop.fk_loop(*args)
-    for halo in (1, 3, 4):
-        got = slab.fk_loop(*args, halo=halo)
-        assert np.array_equal(got["state"], ref["state"]), halo
+    for halo, driver in ((1, "p2p"), (3, "native"), (4, "torch"), (4, "p2p")):
+        got = slab.fk_loop(*args, halo=halo, driver=driver)
+        assert np.array_equal(got["state"], ref["state"]), (halo, driver)
         assert abs(got["volume"] - ref["volume"]) <= 1e-12 * ref["volume"]
     P0, N0, S0 = u0, 0.3 * u0[::-1], np.ones(shape)
     a2 = (P0, N0, S0, wm, gm, 0.1, 0.9, 1.0, 10.0, 1.3, 0.3, 0.35, 0.5, 0.05, 0.02, 1.0, 1.1, 0.9, 9)

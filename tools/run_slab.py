@@ -15,7 +15,7 @@ def main():
     ap.add_argument("--halo", type=int, default=4)
     ap.add_argument("--precision", default="fp64")
     ap.add_argument("--factor", type=float, default=2.0)
-    ap.add_argument("--driver", default="native", choices=["native", "torch"])
+    ap.add_argument("--driver", default="p2p", choices=["native", "torch", "p2p"])
     ap.add_argument("--check", action="store_true", help="compare with the undecomposed loop on rank 0 (small --steps)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))

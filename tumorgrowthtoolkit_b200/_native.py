@@ -70,6 +70,11 @@ def lib():
     L.tgtk_sim_upload.argtypes = [vp, ctypes.c_int, vp, _I64x3, ctypes.c_int]
     L.tgtk_sim_download.argtypes = [vp, ctypes.c_int, vp, _I64x3]
     L.tgtk_sim_prepare.argtypes = [vp]
+    L.tgtk_sim_create_ex.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(Params), ctypes.c_int, vp, ctypes.c_int]
+    L.tgtk_sim_ipc_export.argtypes = [vp, ctypes.c_char_p]
+    L.tgtk_sim_ipc_connect.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+    L.tgtk_sim_run_slab_p2p.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    L.tgtk_sim_slab_error.argtypes = [vp, ctypes.POINTER(ctypes.c_int)]
     L.tgtk_sim_run_slab.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.tgtk_nccl_unique_id.argtypes = [ctypes.c_char_p]
     L.tgtk_nccl_comm_create.argtypes = [ctypes.POINTER(vp), ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
@@ -134,12 +139,12 @@ def make_params(model, dtype, shape, h, dt, rho=0.0, Dw=0.0, ratio=1.0, th_matte
 class Sim:
     """One device-resident simulation (tgtk_sim*)."""
 
-    def __init__(self, params, device=0, stream=None):
+    def __init__(self, params, device=0, stream=None, ipc=False):
         self._h = ctypes.c_void_p()
         self.params = params
         self.shape = (params.X, params.Y, params.Z)
-        _check(lib().tgtk_sim_create(ctypes.byref(self._h), ctypes.byref(params), int(device),
-                                     ctypes.c_void_p(stream) if stream else None))
+        _check(lib().tgtk_sim_create_ex(ctypes.byref(self._h), ctypes.byref(params), int(device),
+                                        ctypes.c_void_p(stream) if stream else None, 1 if ipc else 0))
 
     def close(self):
         if self._h:
@@ -175,6 +180,24 @@ class Sim:
 
     def run_slab(self, comm, nsteps, halo, owned, prev, nxt):
         _check(lib().tgtk_sim_run_slab(self._h, comm, int(nsteps), int(halo), int(owned), int(prev), int(nxt)))
+
+    IPC_BYTES = 7 * 64
+
+    def ipc_export(self):
+        buf = ctypes.create_string_buffer(self.IPC_BYTES)
+        _check(lib().tgtk_sim_ipc_export(self._h, buf))
+        return buf.raw
+
+    def ipc_connect(self, prev, nxt, same_peer=False):
+        _check(lib().tgtk_sim_ipc_connect(self._h, prev, nxt, 1 if same_peer else 0))
+
+    def run_slab_p2p(self, nsteps, halo, owned):
+        _check(lib().tgtk_sim_run_slab_p2p(self._h, int(nsteps), int(halo), int(owned)))
+
+    def slab_error(self):
+        e = ctypes.c_int(0)
+        _check(lib().tgtk_sim_slab_error(self._h, ctypes.byref(e)))
+        return e.value
 
     def set_sum_range(self, x0, x1):
         _check(lib().tgtk_sim_set_sum_range(self._h, int(x0), int(x1)))

@@ -70,6 +70,13 @@ struct tgtk_sim {
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // by parity of the first step
     cudaGraphExec_t slab_graph[2] = {nullptr, nullptr};   // tgtk_sim_run_slab: one block, by parity
     void *slab_key_comm = nullptr; int slab_key_halo = 0, slab_key_owned = 0; double *slab_key_vol = nullptr;
+    // peer-to-peer slab mode: state buffers from cudaMalloc (exportable with CUDA IPC), the neighbours'
+    // buffers and flag words mapped into this process
+    bool ipc = false;
+    int *slab_flags = nullptr;             // [0..1] done epoch from prev/next, [2..3] pushed epoch, [4] error, [5..6] own counters
+    void *peer_state[2][2][3] = {};        // [prev|next][ping-pong][field]
+    int *peer_flags[2] = {nullptr, nullptr};
+    void *peer_opened[2][7] = {};          // pointers to close with cudaIpcCloseMemHandle
     bool host_sched = false;   // no stop criterion: parity baked into launches (see StepArgs)
     int sum_x0 = 0, sum_x1 = -1;     // planes counted in the volume (-1: all)
     int cur_par = 0, cur_slot = 0;   // launch-time values of StepArgs::par / slot
@@ -365,6 +372,8 @@ template <typename T> static const void *v3_kernel(int model, bool wide, int min
     }
 }
 
+static void slab_p2p_close(tgtk_sim *s);
+
 static void drop_graph(tgtk_sim *s)
 {
     for (int i = 0; i < 2; ++i) {
@@ -622,6 +631,11 @@ int tgtk_device_count(int *count)
 
 int tgtk_sim_create(tgtk_sim **out, const tgtk_params *params, int device, void *stream)
 {
+    return tgtk_sim_create_ex(out, params, device, stream, 0);
+}
+
+int tgtk_sim_create_ex(tgtk_sim **out, const tgtk_params *params, int device, void *stream, int flags)
+{
     if (!out || !params) return fail("tgtk_sim_create", "null argument");
     const tgtk_params &p = *params;
     if (p.X < 1 || p.Y < 1 || p.Z < 1) return fail("tgtk_sim_create", "empty box");
@@ -633,6 +647,7 @@ int tgtk_sim_create(tgtk_sim **out, const tgtk_params *params, int device, void 
     tgtk_sim *s = new (std::nothrow) tgtk_sim();
     if (!s) return fail("tgtk_sim_create", "out of host memory");
     s->p = p;
+    s->ipc = (flags & TGTK_CREATE_IPC) != 0;
     s->device = device;
     if (stream) {
         s->stream = (cudaStream_t)stream;
@@ -666,7 +681,8 @@ int tgtk_sim_create(tgtk_sim **out, const tgtk_params *params, int device, void 
     const size_t bytes = (size_t)p.X * s->sx * s->elem;
     for (int b = 0; b < 2; ++b)
         for (int f = 0; f < s->nfields; ++f) {
-            CU(sim_malloc(s, (void **)(&s->state[b][f]), bytes));
+            if (s->ipc) CU(cudaMalloc(&s->state[b][f], bytes));   // pool memory cannot be exported over IPC
+            else CU(sim_malloc(s, (void **)(&s->state[b][f]), bytes));
             CU(cudaMemsetAsync(s->state[b][f], 0, bytes, s->stream));
         }
     for (int c = 0; c < s->ncoef; ++c) {
@@ -693,7 +709,10 @@ void tgtk_sim_destroy(tgtk_sim *s)
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (int b = 0; b < 2; ++b)
-        for (int f = 0; f < 3; ++f) sim_free(s, s->state[b][f]);
+        for (int f = 0; f < 3; ++f) {
+            if (s->ipc) cudaFree(s->state[b][f]);
+            else sim_free(s, s->state[b][f]);
+        }
     for (int c = 0; c < 12; ++c) sim_free(s, s->coef[c]);
     for (void *q : s->snaps) sim_free(s, q);
     sim_free(s, s->stage);
@@ -707,6 +726,7 @@ void tgtk_sim_destroy(tgtk_sim *s)
     sim_free(s, s->partials);
     sim_free(s, s->volumes);
     pinned_ctrl_put(s->ctrl_host);
+    slab_p2p_close(s);
     drop_graph(s);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);

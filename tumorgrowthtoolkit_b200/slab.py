@@ -12,8 +12,11 @@ that exceed one GPU's useful working set, e.g. the 2x up-sampled 480x480x310 atl
     outermost ghost planes are stale, the owned planes never are (overlapped halo recompute).
     One exchange per `halo` steps amortises its latency, which for a 1/8 slab is longer than a
     step (SURVEY.md 7 "halo latency");
-  * the exchange is in place on the simulation's own device buffers: NCCL send/recv (or gloo in
-    the CPU tests) on views of the owned boundary planes / ghost planes -- no staging copies;
+  * the exchange is in place on the simulations' own device buffers, no staging copies.  Three
+    drivers: "p2p" (default) maps the neighbours' buffers with CUDA IPC and PUSHES the owned boundary
+    planes into their ghost planes over NVLink, fenced by epoch flags in peer memory -- no NCCL, the
+    whole block replayed from a CUDA graph; "native" enqueues grouped ncclSend/ncclRecv from C;
+    "torch" uses torch.distributed send/recv per block (NCCL on GPU tensors, gloo in the CPU tests);
   * volumes are summed over owned planes only (tgtk_sim_set_sum_range) and all-reduced once.
 
 Only runs without a volume stop criterion are supported here (stopping_volume = inf).
@@ -112,7 +115,7 @@ class _RawCuda:
 class CudaSlabStepper:
     """One rank's extended slab as a libtgtk_b200 simulation on torch's current CUDA stream."""
 
-    def __init__(self, plan, params, uploads, state_fields, device):
+    def __init__(self, plan, params, uploads, state_fields, device, ipc=False):
         import torch
         from . import _native as nat
         self.torch, self.nat, self.plan, self.device = torch, nat, plan, device
@@ -120,7 +123,7 @@ class CudaSlabStepper:
         # a dedicated torch stream: the library launches on it and torch.distributed orders its
         # NCCL transfers after / before the work of the stream that is current when they are issued
         self.tstream = torch.cuda.Stream(device=device)
-        self.sim = nat.Sim(params, device, stream=self.tstream.cuda_stream)
+        self.sim = nat.Sim(params, device, stream=self.tstream.cuda_stream, ipc=ipc)
         for field, arr in uploads:
             self.sim.upload(field, arr)
         self.sim.prepare()
@@ -196,7 +199,7 @@ def _native_comm(dist, rank, world, device):
     return _COMMS[key]
 
 
-def _run_cuda(model, fields_in, statics, scalars, shape, h, dt, nsteps, halo, precision, device, names, driver="native"):
+def _run_cuda(model, fields_in, statics, scalars, shape, h, dt, nsteps, halo, precision, device, names, driver="p2p"):
     import torch
     from . import _native as nat
     from ._loop import dtype_code
@@ -205,11 +208,27 @@ def _run_cuda(model, fields_in, statics, scalars, shape, h, dt, nsteps, halo, pr
     local_shape = (plan.local_planes,) + tuple(shape[1:])
     p = nat.make_params(model, dtype_code(precision), local_shape, h, dt, **scalars)
     uploads = [(f, plan.extend(a)) for f, a in statics] + [(f, plan.extend(a)) for f, a in fields_in]
-    stepper = CudaSlabStepper(plan, p, uploads, [f for f, _ in fields_in], device)
+    stepper = CudaSlabStepper(plan, p, uploads, [f for f, _ in fields_in], device, ipc=(driver == "p2p"))
     # device time of the whole decomposed loop (step kernels + halo exchanges) on this rank
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stepper.tstream)
-    if driver == "native":
+    if driver == "p2p":
+        # peer-to-peer pushes over NVLink: map the neighbours' buffers (CUDA IPC handles travel over the
+        # caller's torch.distributed group), then the library enqueues steps + pushes + handshakes
+        mine = stepper.sim.ipc_export()
+        if world > 1:
+            t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(f"cuda:{device}")
+            allh = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(allh, t)
+            hb = [bytes(h.cpu().numpy().tobytes()) for h in allh]
+            stepper.sim.ipc_connect(hb[plan.prev], hb[plan.next], same_peer=(plan.prev == plan.next))
+            dist.barrier()
+        else:
+            stepper.sim.ipc_connect(None, None)
+        ev0.record(stepper.tstream)
+        stepper.sim.run_slab_p2p(nsteps, plan.halo, plan.n)
+        stepper.steps = nsteps
+    elif driver == "native":
         # the whole loop (steps + NCCL ring exchanges) enqueued by the library on the sim's stream
         comm = _native_comm(dist, rank, world, device) if world > 1 else None
         stepper.sim.run_slab(comm, nsteps, plan.halo, plan.n, plan.prev, plan.next)
@@ -217,6 +236,13 @@ def _run_cuda(model, fields_in, statics, scalars, shape, h, dt, nsteps, halo, pr
     else:
         run_blocks(plan, stepper, nsteps, dist)       # torch.distributed send/recv per block
     ev1.record(stepper.tstream)
+    if driver == "p2p":
+        stepper.tstream.synchronize()
+        err = stepper.sim.slab_error()
+        if world > 1:
+            dist.barrier()          # nobody unmaps buffers a neighbour may still be pushing into
+        if err:
+            raise nat.NativeError(f"peer-to-peer halo handshake {err} timed out (a neighbouring rank stalled)")
     st, vols, owned = stepper.finish()
     loop_ms = ev0.elapsed_time(ev1)
     if world > 1:
@@ -231,7 +257,7 @@ def _run_cuda(model, fields_in, statics, scalars, shape, h, dt, nsteps, halo, pr
     return res
 
 
-def fk_loop(u0, WM, GM, th, Dw, ratio, rho, dt, dx, dy, dz, nsteps, halo=4, precision="fp64", device=0, driver="native"):
+def fk_loop(u0, WM, GM, th, Dw, ratio, rho, dt, dx, dy, dz, nsteps, halo=4, precision="fp64", device=0, driver="p2p"):
     """FK.py:200,212-226 on a slab-decomposed grid (all ranks pass the same global arrays)."""
     from . import _native as nat
     return _run_cuda(nat.MODEL_FK, [(nat.FIELD_U, u0)], [(nat.FIELD_WM, WM), (nat.FIELD_GM, GM)],
@@ -239,7 +265,7 @@ def fk_loop(u0, WM, GM, th, Dw, ratio, rho, dt, dx, dy, dz, nsteps, halo=4, prec
                      precision, device, ("u",), driver)
 
 
-def dti_loop(u0, rgb, Dw, rho, dt, dx, dy, dz, nsteps, halo=4, precision="fp64", device=0, driver="native"):
+def dti_loop(u0, rgb, Dw, rho, dt, dx, dy, dz, nsteps, halo=4, precision="fp64", device=0, driver="p2p"):
     """FK_DTI.py:174,195-214 on a slab-decomposed grid (without the `volume < 1e-6` exit)."""
     from . import _native as nat
     rgb = np.asarray(rgb)
@@ -249,7 +275,7 @@ def dti_loop(u0, rgb, Dw, rho, dt, dx, dy, dz, nsteps, halo=4, precision="fp64",
 
 
 def fk2c_loop(P0, N0, S0, WM, GM, th, th_necro, Dw, ratio, Ds, rho, lambda_np, sigma_np, lambda_s, dt, dx, dy, dz,
-              nsteps, halo=4, precision="fp64", device=0, driver="native"):
+              nsteps, halo=4, precision="fp64", device=0, driver="p2p"):
     """FK_2c.py:215-216,227-245 on a slab-decomposed grid: P, N and S halos are exchanged."""
     from . import _native as nat
     return _run_cuda(nat.MODEL_FK_2C, [(nat.FIELD_P, P0), (nat.FIELD_N, N0), (nat.FIELD_S, S0)],
