@@ -152,12 +152,12 @@ int tgtk_sim_run_slab(tgtk_sim *sim, void *comm, int nsteps, int halo, int owned
  *   tgtk_sim_ipc_export : TGTK_IPC_BYTES bytes describing this rank's buffers (send to neighbours)
  *   tgtk_sim_ipc_connect: map the previous / next rank's buffers (same_peer: world == 2, both
  *                          neighbours are one process; NULL handles: world == 1)
- * The simulation must have been created with TGTK_CREATE_IPC.  Spin-waits are bounded (about two
- * seconds); a time-out sets an error that tgtk_sim_sync reports. */
+ * prev_owned: planes the previous rank owns (slabs differ by one plane when axis 0 does not divide).
+ * The simulation must have been created with TGTK_CREATE_IPC.  Spin-waits are bounded (20 s); a time-out sets an error that tgtk_sim_sync reports. */
 #define TGTK_IPC_BYTES (7 * 64)
 int tgtk_sim_ipc_export(tgtk_sim *sim, unsigned char *out);
 int tgtk_sim_ipc_connect(tgtk_sim *sim, const unsigned char *prev, const unsigned char *next, int same_peer);
-int tgtk_sim_run_slab_p2p(tgtk_sim *sim, int nsteps, int halo, int owned);
+int tgtk_sim_run_slab_p2p(tgtk_sim *sim, int nsteps, int halo, int owned, int prev_owned);
 /* 0, or which handshake of the peer-to-peer driver timed out (1: block done, 2: ghosts pushed). */
 int tgtk_sim_slab_error(tgtk_sim *sim, int *err);
 

@@ -27,13 +27,14 @@ def _torchrun(n, script, *args, port=29561):
 
 
 @pytest.mark.parametrize("driver", ["p2p", "native", "torch"])
-@pytest.mark.parametrize("model", ["dti", "fk2c"])
-def test_slab_two_ranks_is_bitwise(model, driver):
-    if _ngpus() < 2:
-        pytest.skip("needs 2 GPUs")
-    r = _torchrun(2, "run_slab.py", "--model", model, "--steps", "13", "--halo", "3", "--factor", "0.5", "--check",
+@pytest.mark.parametrize("model,world", [("dti", 2), ("fk2c", 2), ("dti", 4)])
+def test_slab_ranks_are_bitwise(model, world, driver):
+    """74 planes over 4 ranks = 19,19,18,18: uneven slabs exercise the neighbour-specific ghost offsets."""
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    r = _torchrun(world, "run_slab.py", "--model", model, "--steps", "13", "--halo", "3", "--factor", "0.5", "--check",
                   "--driver", driver)
-    assert r["n_gpus"] == 2 and r["max_abs_diff_vs_undecomposed"] == 0.0
+    assert r["n_gpus"] == world and r["max_abs_diff_vs_undecomposed"] == 0.0
     assert r["volume_rel_diff"] <= 1e-12
 
 

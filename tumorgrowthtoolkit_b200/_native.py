@@ -73,7 +73,7 @@ def lib():
     L.tgtk_sim_create_ex.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(Params), ctypes.c_int, vp, ctypes.c_int]
     L.tgtk_sim_ipc_export.argtypes = [vp, ctypes.c_char_p]
     L.tgtk_sim_ipc_connect.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
-    L.tgtk_sim_run_slab_p2p.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    L.tgtk_sim_run_slab_p2p.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.tgtk_sim_slab_error.argtypes = [vp, ctypes.POINTER(ctypes.c_int)]
     L.tgtk_sim_run_slab.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.tgtk_nccl_unique_id.argtypes = [ctypes.c_char_p]
@@ -191,8 +191,8 @@ class Sim:
     def ipc_connect(self, prev, nxt, same_peer=False):
         _check(lib().tgtk_sim_ipc_connect(self._h, prev, nxt, 1 if same_peer else 0))
 
-    def run_slab_p2p(self, nsteps, halo, owned):
-        _check(lib().tgtk_sim_run_slab_p2p(self._h, int(nsteps), int(halo), int(owned)))
+    def run_slab_p2p(self, nsteps, halo, owned, prev_owned):
+        _check(lib().tgtk_sim_run_slab_p2p(self._h, int(nsteps), int(halo), int(owned), int(prev_owned)))
 
     def slab_error(self):
         e = ctypes.c_int(0)

@@ -226,7 +226,7 @@ def _run_cuda(model, fields_in, statics, scalars, shape, h, dt, nsteps, halo, pr
         else:
             stepper.sim.ipc_connect(None, None)
         ev0.record(stepper.tstream)
-        stepper.sim.run_slab_p2p(nsteps, plan.halo, plan.n)
+        stepper.sim.run_slab_p2p(nsteps, plan.halo, plan.n, plan.sizes[plan.prev])
         stepper.steps = nsteps
     elif driver == "native":
         # the whole loop (steps + NCCL ring exchanges) enqueued by the library on the sim's stream
