@@ -86,7 +86,8 @@ struct tgtk_sim {
     std::vector<int> snap_steps;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
-    int64_t launches = 0;
+    int64_t launches = 0;       // step-kernel launches (graph nodes included)
+    int64_t aux_launches = 0;   // chunk reductions and other helper kernels, as enqueued or captured
 };
 
 // Device memory comes from the stream-ordered allocator: unlike cudaMalloc / cudaFree it never
@@ -498,6 +499,7 @@ static cudaError_t launch_one(tgtk_sim *s, int par, int slot)
 static cudaError_t launch_chunk_finish(tgtk_sim *s, int count)
 {
     const tgtk_params &p = s->p;
+    ++s->aux_launches;
     chunk_finish_kernel<<<count, 256, 0, s->stream>>>(s->ctrl, s->partials, s->volumes, s->volumes_cap, s->nblocks, s->nfields,
                                                    count, p.h[0] * p.h[1] * p.h[2], 1.0);
     return cudaGetLastError();
