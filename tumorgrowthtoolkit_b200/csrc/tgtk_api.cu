@@ -63,6 +63,7 @@ struct tgtk_sim {
     bool prepared = false;
     int variant = 0;       // 0: auto (default), 1: baseline, 2: marching via L1, 3: marching via shared memory
     int lx = 1;            // planes per block of the marching kernels
+    double narrow_penalty = 0.25;   // 16-wide v4 tiles are chosen when they waste this much less than 32-wide
     int v4_threads = 128;  // fk2c_step_v4 block size: 128 (32x4 threads, 32x8 voxels) or 256 (32x8 threads, 32x16 voxels)
     int pf = 1;            // FK_2c staged kernel: prefetch distance in planes (1: two register sets, 4 blocks/SM; 2: three sets)
     int force_tz = 0;      // 0: pick the tile width by lane waste
@@ -281,18 +282,23 @@ template <typename T> static cudaError_t launch_step(tgtk_sim *s)
     StepArgs<T> a;
     fill_args(s, a);
     if (s->lx > 0 && effective_variant(s) == 4 && s->p.model == TGTK_MODEL_FK) {
-        if (s->block.y == 4) fk_step_v4<T, 32, 4, 8><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+        if (s->block.x == 16) fk_step_v4<T, 16, 8, 8><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+        else if (s->block.y == 4) fk_step_v4<T, 32, 4, 8><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
         else fk_step_v4<T, 32, 8, 4><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
         return cudaGetLastError();
     }
     if (s->lx > 0 && effective_variant(s) == 4 && s->p.model == TGTK_MODEL_DTI) {
-        if (s->block.y == 4) dti_step_v4<T, 32, 4, 8><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+        if (s->block.x == 16) dti_step_v4<T, 16, 8, 8><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+        else if (s->block.y == 4) dti_step_v4<T, 32, 4, 8><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
         else dti_step_v4<T, 32, 8, 4><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
         return cudaGetLastError();
     }
     if (s->lx > 0 && effective_variant(s) == 4 && s->p.model == TGTK_MODEL_FK_2C) {   // two voxels per thread
         const int mb = s->minb ? s->minb : ((sizeof(T) == 8) ? 2 : 3);
-        if (s->block.y == 4) {
+        if (s->block.x == 16) {
+            if (mb >= 3) fk2c_step_v4<T, 16, 8, 6><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+            else fk2c_step_v4<T, 16, 8, 4><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+        } else if (s->block.y == 4) {
             if (mb >= 3) fk2c_step_v4<T, 32, 4, 6><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
             else fk2c_step_v4<T, 32, 4, 4><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
         } else {
@@ -387,6 +393,13 @@ static void drop_graph(tgtk_sim *s)
 
 static const void *v4_kernel(int model, int dtype, int rows, int minb)
 {
+    if (rows == 16) {   // 16-wide tiles
+        if (model == TGTK_MODEL_FK) return dtype == TGTK_F64 ? (const void *)fk_step_v4<double, 16, 8, 8> : (const void *)fk_step_v4<float, 16, 8, 8>;
+        if (model == TGTK_MODEL_DTI) return dtype == TGTK_F64 ? (const void *)dti_step_v4<double, 16, 8, 8> : (const void *)dti_step_v4<float, 16, 8, 8>;
+        const int mb = minb ? minb : ((dtype == TGTK_F64) ? 2 : 3);
+        if (dtype == TGTK_F64) return mb >= 3 ? (const void *)fk2c_step_v4<double, 16, 8, 6> : (const void *)fk2c_step_v4<double, 16, 8, 4>;
+        return mb >= 3 ? (const void *)fk2c_step_v4<float, 16, 8, 6> : (const void *)fk2c_step_v4<float, 16, 8, 4>;
+    }
     if (model == TGTK_MODEL_FK) {
         if (dtype == TGTK_F64) return rows == 4 ? (const void *)fk_step_v4<double, 32, 4, 8> : (const void *)fk_step_v4<double, 32, 8, 4>;
         return rows == 4 ? (const void *)fk_step_v4<float, 32, 4, 8> : (const void *)fk_step_v4<float, 32, 8, 4>;
@@ -426,18 +439,26 @@ static int configure_launch(tgtk_sim *s)
             if (cost < best) { best = cost; best_tz = tz; }
         }
         const bool two_rows = (variant == 4);   // *_step_v4: 32 x 8 or 32 x 16 voxel tile, two rows per thread
-        const int v4rows = (s->v4_threads == 128) ? 4 : 8;                       // thread rows; voxel rows = 2x
-        const int tz = two_rows ? 32 : best_tz, ty = two_rows ? 2 * v4rows : 256 / tz;
+        // v4 tiles: 32(z) x 8(y) voxels on 32x4 threads, 16 x 16 voxels on 16x8 threads (narrow boxes waste
+        // fewer lanes), or 32 x 16 voxels on 32x8 threads (TGTK_V4_THREADS=256)
+        bool narrow = false;
+        if (two_rows && s->v4_threads == 128) {
+            const double w32 = (double)((p.Z + 31) / 32 * 32) * ((p.Y + 7) / 8 * 8);
+            const double w16 = (double)((p.Z + 15) / 16 * 16) * ((p.Y + 15) / 16 * 16);
+            narrow = s->force_tz ? (s->force_tz == 16) : (w16 * (1.0 + s->narrow_penalty) < w32);
+        }
+        const int v4rows = narrow ? 8 : ((s->v4_threads == 128) ? 4 : 8);          // thread rows; voxel rows = 2x
+        const int tz = two_rows ? (narrow ? 16 : 32) : best_tz, ty = two_rows ? 2 * v4rows : 256 / tz;
         const int tiles = ((p.Z + tz - 1) / tz) * ((p.Y + ty - 1) / ty);
         // Segment length: trade the tail of the last wave (blocks / resident slots not an
         // integer) against the two extra planes every segment loads to prime its pipeline.
         int per_sm = 2, sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
-        const void *fn = two_rows ? v4_kernel(p.model, p.dtype, v4rows, s->minb)
+        const void *fn = two_rows ? v4_kernel(p.model, p.dtype, narrow ? 16 : v4rows, s->minb)
                          : (variant >= 3)
                              ? ((p.dtype == TGTK_F64) ? v3_kernel<double>(p.model, tz == 32, s->pf == 1 ? 14 : s->minb) : v3_kernel<float>(p.model, tz == 32, s->pf == 1 ? 14 : s->minb))
                              : ((p.dtype == TGTK_F64) ? v2_kernel<double>(p.model) : v2_kernel<float>(p.model));
-        const int nthreads = two_rows ? 32 * v4rows : 256;
+        const int nthreads = two_rows ? tz * v4rows : 256;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, nthreads, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
         const double slots = (double)sms * per_sm;
         int best_lx = p.X;
@@ -676,6 +697,7 @@ int tgtk_sim_create_ex(tgtk_sim **out, const tgtk_params *params, int device, vo
     if (const char *v = getenv("TGTK_MINB")) s->minb = atoi(v);
     if (const char *v = getenv("TGTK_PF")) s->pf = atoi(v);
     if (const char *v = getenv("TGTK_V4_THREADS")) s->v4_threads = atoi(v);
+    if (const char *v = getenv("TGTK_NARROW_PENALTY")) s->narrow_penalty = atof(v);
     if (const char *v = getenv("TGTK_GRAPH")) s->use_graph = atoi(v) != 0;
     if (const char *v = getenv("TGTK_TZ")) s->force_tz = atoi(v);
     *out = s;  // from here on tgtk_sim_destroy cleans up on failure
