@@ -7,6 +7,21 @@ from hypothesis import given, settings, strategies as st, HealthCheck
 pytestmark = pytest.mark.gpu
 
 shapes = st.tuples(st.integers(1, 40), st.integers(1, 40), st.integers(1, 70))
+# library tunables read at tgtk_sim_create: L2 prefetch distance (-1 auto, 0 off) and programmatic dependent launch
+tunables = st.tuples(st.sampled_from([-1, 0, 1, 2, 5]), st.sampled_from([0, 1]))
+
+
+def _set_tunables(t):
+    import os
+    os.environ["TGTK_L2PF"], os.environ["TGTK_PDL"] = str(t[0]), str(t[1])
+
+
+@pytest.fixture(autouse=True)
+def _restore_env():
+    import os
+    yield
+    os.environ.pop("TGTK_L2PF", None)
+    os.environ.pop("TGTK_PDL", None)
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -17,9 +32,10 @@ def _built():
 
 @settings(max_examples=30, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
 @given(shape=shapes, seed=st.integers(0, 2 ** 20), variant=st.sampled_from([1, 2, 3, 4]),
-       h=st.tuples(st.floats(0.5, 2.0), st.floats(0.5, 2.0), st.floats(0.5, 2.0)), nsteps=st.integers(1, 6))
-def test_fk_and_fk2c_any_box(oracle, shape, seed, variant, h, nsteps):
+       h=st.tuples(st.floats(0.5, 2.0), st.floats(0.5, 2.0), st.floats(0.5, 2.0)), nsteps=st.integers(1, 6), tun=tunables)
+def test_fk_and_fk2c_any_box(oracle, shape, seed, variant, h, nsteps, tun):
     from tumorgrowthtoolkit_b200 import _native as nat
+    _set_tunables(tun)
     rng = np.random.default_rng(seed)
     wm = rng.uniform(0, 1, shape) * (rng.uniform(0, 1, shape) < 0.8)
     gm = rng.uniform(0, 1, shape) * (1 - wm)
@@ -58,9 +74,10 @@ def test_fk_and_fk2c_any_box(oracle, shape, seed, variant, h, nsteps):
 
 
 @settings(max_examples=15, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
-@given(shape=shapes, seed=st.integers(0, 2 ** 20), variant=st.sampled_from([1, 2, 3, 4]), nsteps=st.integers(1, 5))
-def test_dti_any_box_bitwise(oracle, shape, seed, variant, nsteps):
+@given(shape=shapes, seed=st.integers(0, 2 ** 20), variant=st.sampled_from([1, 2, 3, 4]), nsteps=st.integers(1, 5), tun=tunables)
+def test_dti_any_box_bitwise(oracle, shape, seed, variant, nsteps, tun):
     from tumorgrowthtoolkit_b200 import _native as nat
+    _set_tunables(tun)
     rng = np.random.default_rng(seed)
     rgb = rng.uniform(0, 3, shape + (3,)) * (rng.uniform(0, 1, shape) < 0.8)[..., None]
     u0 = rng.uniform(0, 1, shape)

@@ -67,6 +67,11 @@ struct tgtk_sim {
     int v4_threads = 128;  // fk2c_step_v4 block size: 128 (32x4 threads, 32x8 voxels) or 256 (32x8 threads, 32x16 voxels)
     int pf = 1;            // FK_2c staged kernel: prefetch distance in planes (1: two register sets, 4 blocks/SM; 2: three sets)
     int force_tz = 0;      // 0: pick the tile width by lane waste
+    int l2pf = -1;         // v4 kernels: L2 prefetch distance in planes (TGTK_L2PF); 0 = off, -1 = auto:
+                           // 2 planes when the arrays a step touches do not fit in L2, else off (measured:
+                           // the requests only cost time when the working set is L2 resident)
+    int l2_bytes = 0;      // cudaDevAttrL2CacheSize
+    int pdl = 1;           // host-scheduled v4 launches overlap their prologue with the previous step (TGTK_PDL=0: off)
     bool use_graph = true;
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // by parity of the first step
     cudaGraphExec_t slab_graph[2] = {nullptr, nullptr};   // tgtk_sim_run_slab: one block, by parity
@@ -267,6 +272,12 @@ template <typename T> static void fill_args(const tgtk_sim *s, StepArgs<T> &a)
     a.slot = s->cur_slot;
     a.sum_x0 = s->sum_x0;
     a.sum_x1 = (s->sum_x1 < 0) ? p.X : s->sum_x1;
+    int l2pf = s->l2pf;
+    if (l2pf < 0) {
+        const double touched = (double)(2 * s->nfields + s->ncoef) * (double)p.X * (double)s->sx * (double)s->elem;
+        l2pf = (touched > 0.8 * (double)s->l2_bytes) ? 2 : 0;
+    }
+    a.l2pf = (l2pf > 0 && l2pf < p.X) ? l2pf : 0;
 }
 
 // variant 0 = auto = the staged kernels with two voxels per thread (v4), fastest for every model and
@@ -277,33 +288,51 @@ static int effective_variant(const tgtk_sim *s)
     return 4;
 }
 
+// v4 launches go through cudaLaunchKernelEx so that host-scheduled steps can carry the programmatic
+// stream serialization attribute (PDL): step t+1 is scheduled while step t drains, runs its index set-up
+// and static-coefficient loads, and blocks in griddepcontrol.wait until step t has completed and flushed.
+template <typename... KA, typename... A> static cudaError_t launch_v4(tgtk_sim *s, void (*kern)(KA...), A... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = s->grid;
+    cfg.blockDim = s->block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (s->pdl && s->host_sched && s->cur_slot > 0) ? 1 : 0;   // slot 0 follows a non-step node
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 template <typename T> static cudaError_t launch_step(tgtk_sim *s)
 {
     StepArgs<T> a;
     fill_args(s, a);
     if (s->lx > 0 && effective_variant(s) == 4 && s->p.model == TGTK_MODEL_FK) {
-        if (s->block.x == 16) fk_step_v4<T, 16, 8, 8><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
-        else if (s->block.y == 4) fk_step_v4<T, 32, 4, 8><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
-        else fk_step_v4<T, 32, 8, 4><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+        if (s->block.x == 16) return launch_v4(s, fk_step_v4<T, 16, 8, 8>, a, s->lx);
+        else if (s->block.y == 4) return launch_v4(s, fk_step_v4<T, 32, 4, 8>, a, s->lx);
+        else return launch_v4(s, fk_step_v4<T, 32, 8, 4>, a, s->lx);
         return cudaGetLastError();
     }
     if (s->lx > 0 && effective_variant(s) == 4 && s->p.model == TGTK_MODEL_DTI) {
-        if (s->block.x == 16) dti_step_v4<T, 16, 8, 8><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
-        else if (s->block.y == 4) dti_step_v4<T, 32, 4, 8><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
-        else dti_step_v4<T, 32, 8, 4><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+        if (s->block.x == 16) return launch_v4(s, dti_step_v4<T, 16, 8, 8>, a, s->lx);
+        else if (s->block.y == 4) return launch_v4(s, dti_step_v4<T, 32, 4, 8>, a, s->lx);
+        else return launch_v4(s, dti_step_v4<T, 32, 8, 4>, a, s->lx);
         return cudaGetLastError();
     }
     if (s->lx > 0 && effective_variant(s) == 4 && s->p.model == TGTK_MODEL_FK_2C) {   // two voxels per thread
         const int mb = s->minb ? s->minb : ((sizeof(T) == 8) ? 2 : 3);
         if (s->block.x == 16) {
-            if (mb >= 3) fk2c_step_v4<T, 16, 8, 6><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
-            else fk2c_step_v4<T, 16, 8, 4><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+            if (mb >= 3) return launch_v4(s, fk2c_step_v4<T, 16, 8, 6>, a, s->lx);
+            else return launch_v4(s, fk2c_step_v4<T, 16, 8, 4>, a, s->lx);
         } else if (s->block.y == 4) {
-            if (mb >= 3) fk2c_step_v4<T, 32, 4, 6><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
-            else fk2c_step_v4<T, 32, 4, 4><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+            if (mb >= 3) return launch_v4(s, fk2c_step_v4<T, 32, 4, 6>, a, s->lx);
+            else return launch_v4(s, fk2c_step_v4<T, 32, 4, 4>, a, s->lx);
         } else {
-            if (mb >= 3) fk2c_step_v4<T, 32, 8, 3><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
-            else fk2c_step_v4<T, 32, 8, 2><<<s->grid, s->block, 0, s->stream>>>(a, s->lx);
+            if (mb >= 3) return launch_v4(s, fk2c_step_v4<T, 32, 8, 3>, a, s->lx);
+            else return launch_v4(s, fk2c_step_v4<T, 32, 8, 2>, a, s->lx);
         }
         return cudaGetLastError();
     }
@@ -700,6 +729,9 @@ int tgtk_sim_create_ex(tgtk_sim **out, const tgtk_params *params, int device, vo
     if (const char *v = getenv("TGTK_NARROW_PENALTY")) s->narrow_penalty = atof(v);
     if (const char *v = getenv("TGTK_GRAPH")) s->use_graph = atoi(v) != 0;
     if (const char *v = getenv("TGTK_TZ")) s->force_tz = atoi(v);
+    if (const char *v = getenv("TGTK_L2PF")) s->l2pf = atoi(v);
+    if (const char *v = getenv("TGTK_PDL")) s->pdl = atoi(v);
+    if (cudaDeviceGetAttribute(&s->l2_bytes, cudaDevAttrL2CacheSize, s->device) != cudaSuccess) s->l2_bytes = 0;
     *out = s;  // from here on tgtk_sim_destroy cleans up on failure
     if (configure_launch(s)) return 1;
     const size_t bytes = (size_t)p.X * s->sx * s->elem;

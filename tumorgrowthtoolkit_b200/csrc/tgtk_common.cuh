@@ -49,7 +49,59 @@ template <typename T> struct StepArgs {
     int host_sched, par, slot;
     // planes [sum_x0, sum_x1) count towards the volume (slab mode: the owned planes, not the ghosts)
     int sum_x0, sum_x1;
+    // marching kernels: planes ahead of the current one whose lines are requested into L2
+    // (prefetch.global.L2, fire and forget); 0 = off
+    int l2pf;
 };
+
+// L2 prefetch of the rows [y0, y0+rows) of plane xp of one array: rows of a plane are contiguous
+// (axis 2 fastest), so the whole strip -- every z tile of it -- is ONE bulk request to the TMA unit
+// (cp.async.bulk.prefetch.L2), issued by a single thread of the blockIdx.x == 0 tile.  Start and
+// end are rounded to the instruction's 16-byte granularity inside the array.
+template <typename T>
+__device__ __forceinline__ void l2_prefetch_strip(const T *base, uint32_t first, uint32_t count, uint32_t total)
+{
+    const uint64_t b0 = ((uint64_t)first * sizeof(T)) & ~(uint64_t)15;
+    uint64_t b1 = ((uint64_t)(first + count) * sizeof(T) + 15) & ~(uint64_t)15;
+    const uint64_t cap = ((uint64_t)total * sizeof(T)) & ~(uint64_t)15;
+    if (b1 > cap) b1 = cap;
+    if (b1 <= b0) return;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char *)base + b0), "r"((uint32_t)(b1 - b0))
+                 : "memory");
+}
+
+// per-kernel prefetch state of the thread that issues the strips (others: on = false)
+struct L2Strip {
+    bool on;
+    uint32_t row0, count, plane, total;   // elements: offset of the strip in a plane, its length, plane pitch, array size
+};
+template <typename T> __device__ __forceinline__ L2Strip l2_strip_setup(const StepArgs<T> &a, int rows_per_tile)
+{
+    L2Strip s;
+    const int tid = threadIdx.x + blockDim.x * threadIdx.y;
+    s.on = a.l2pf > 0 && blockIdx.x == 0 && tid == 0;
+    const int y0 = blockIdx.y * rows_per_tile;
+    const int rows = min(rows_per_tile, a.Y - y0);
+    s.row0 = (uint32_t)y0 * (uint32_t)a.sy;
+    s.count = (uint32_t)rows * (uint32_t)a.sy;
+    s.plane = (uint32_t)a.sx;
+    s.total = (uint32_t)a.X * (uint32_t)a.sx;
+    return s;
+}
+// element offset of the strip in plane x + l2pf (periodic)
+template <typename T> __device__ __forceinline__ uint32_t l2_strip_at(const StepArgs<T> &a, const L2Strip &s, int x)
+{
+    int xp = x + a.l2pf;
+    if (xp >= a.X) xp -= a.X;
+    return (uint32_t)xp * s.plane + s.row0;
+}
+
+// Programmatic dependent launch (tgtk_api.cu: launch_v4).  Both are no-ops in a launch without the
+// attribute.  griddep_wait() returns once the preceding grid has completed and its writes are visible:
+// nothing that grid writes (the state it produces) or reads (the state this grid overwrites) may be
+// touched before it.
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 template <typename T> __device__ __forceinline__ bool counts(const StepArgs<T> &a, int x)
 {

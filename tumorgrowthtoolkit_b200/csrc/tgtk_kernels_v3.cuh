@@ -339,6 +339,8 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> 
     auto keff = [&](T pq, T nq, T kq) { return (pq + nq <= a.th_necro) ? kq : closed; };
     auto load = [&](Vox2c<T> &v, uint32_t off) { v.p = P[off]; v.n = N[off]; v.s = S[off]; v.b = bc[off]; v.k = kc[off]; };
     double sP = 0.0, sN = 0.0;
+    griddep_launch();
+    griddep_wait();
 
     Vox2c<T> A0, A1, B0, B1;               // rows (y, y+1) of plane x (A) and plane x+1 (B); roles swap
     load(A0, g.c0); A0.k = keff(A0.p, A0.n, A0.k);
@@ -354,6 +356,7 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> 
     T hp = 0, hn = 0, hk = 0, hsv = 0, hb = 0;
     if (g.ring) { hp = P[g.h]; hn = N[g.h]; hk = kc[g.h]; hsv = S[g.h]; hb = bc[g.h]; }
     int buf = 0;
+    const L2Strip pf = l2_strip_setup(a, TYV);
 
     auto step = [&](int x, const Vox2c<T> &c0, const Vox2c<T> &c1, Vox2c<T> &p0, Vox2c<T> &p1) {
         Pair<T>(*tl)[PL] = tile[buf];
@@ -373,6 +376,12 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> 
         load(p1, n1);
         g.h = (x + 1 == a.X) ? g.h - g.wrap_back : g.h + g.sx;
         if (g.ring) { hp = P[g.h]; hn = N[g.h]; hk = kc[g.h]; hsv = S[g.h]; hb = bc[g.h]; }
+        if (pf.on) {                           // this tile strip of plane x + l2pf into L2
+            const uint32_t q = l2_strip_at(a, pf, x);
+            l2_prefetch_strip(P, q, pf.count, pf.total); l2_prefetch_strip(N, q, pf.count, pf.total);
+            l2_prefetch_strip(S, q, pf.count, pf.total); l2_prefetch_strip(kc, q, pf.count, pf.total);
+            l2_prefetch_strip(bc, q, pf.count, pf.total);
+        }
         // work that needs neither neighbours nor plane x+1
         const T H0 = heaviside50_fast(c0.s, a.sigma_np), H1 = heaviside50_fast(c1.s, a.sigma_np);
         const T react0 = a.rho * (c0.s * c0.p) * ((T(1) - c0.p) - c0.n) - (a.lambda_np * c0.p) * H0;
@@ -441,6 +450,8 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk_step_v4(const StepArgs<T> a,
     const T *__restrict__ kc = a.coef[0];
     Stage2 g = stage2_setup<T, TZ, TYT, RS>(a, lx);
     double s = 0.0;
+    griddep_launch();
+    griddep_wait();
 
     VoxFk<T> A0, A1, B0, B1;
     A0.u = u[g.c0]; A0.k = kc[g.c0];
@@ -450,6 +461,7 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk_step_v4(const StepArgs<T> a,
     T hu = 0, hk = 0;
     if (g.ring) { hu = u[g.h]; hk = kc[g.h]; }
     int buf = 0;
+    const L2Strip pf = l2_strip_setup(a, TYV);
 
     auto step = [&](int x, const VoxFk<T> &c0, const VoxFk<T> &c1, VoxFk<T> &p0, VoxFk<T> &p1) {
         Pair<T> *tl = tile[buf];
@@ -463,6 +475,10 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk_step_v4(const StepArgs<T> a,
         p1.u = u[n1]; p1.k = kc[n1];
         g.h = (x + 1 == a.X) ? g.h - g.wrap_back : g.h + g.sx;
         if (g.ring) { hu = u[g.h]; hk = kc[g.h]; }
+        if (pf.on) {
+            const uint32_t q = l2_strip_at(a, pf, x);
+            l2_prefetch_strip(u, q, pf.count, pf.total); l2_prefetch_strip(kc, q, pf.count, pf.total);
+        }
         const T react0 = a.rho * c0.u * (T(1) - c0.u), react1 = a.rho * c1.u * (T(1) - c1.u);
         const T f_mid = relu(c0.k + c1.k) * (c0.u - c1.u);
         __syncthreads();
@@ -512,12 +528,15 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) dti_step_v4(const StepArgs<T> a
     auto load = [&](VoxDti<T> &v, uint32_t off) { v.u = u[off]; v.d0 = dxa[off]; v.d1 = dya[off]; v.d2 = dza[off]; };
 
     VoxDti<T> A0, A1, B0, B1;
+    griddep_launch();
+    griddep_wait();
     load(A0, g.c0);
     load(A1, g.c1);
     T um0 = u[g.prev0], um1 = u[g.prev1];
     T hu = 0;
     if (g.ring) hu = u[g.h];
     int buf = 0;
+    const L2Strip pf = l2_strip_setup(a, TYV);
 
     auto one = [&](const VoxDti<T> &c, T um, T up, T uym, T uyp, T uzm, T uzp) {
         const T sx = R::mul(a.cx, R::sub(R::mul(c.d0, R::sub(um, c.u)), R::mul(c.d0, R::sub(c.u, up))));
@@ -539,6 +558,11 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) dti_step_v4(const StepArgs<T> a
         load(p1, n1);
         g.h = (x + 1 == a.X) ? g.h - g.wrap_back : g.h + g.sx;
         if (g.ring) hu = u[g.h];
+        if (pf.on) {
+            const uint32_t q = l2_strip_at(a, pf, x);
+            l2_prefetch_strip(u, q, pf.count, pf.total); l2_prefetch_strip(dxa, q, pf.count, pf.total);
+            l2_prefetch_strip(dya, q, pf.count, pf.total); l2_prefetch_strip(dza, q, pf.count, pf.total);
+        }
         __syncthreads();
         const T un0 = one(c0, um0, p0.u, tl[o0 - RS], c1.u, tl[o0 - 1], tl[o0 + 1]);
         const T un1 = one(c1, um1, p1.u, c0.u, tl[o1 + RS], tl[o1 - 1], tl[o1 + 1]);
