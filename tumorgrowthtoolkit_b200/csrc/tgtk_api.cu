@@ -15,6 +15,7 @@
 #include "tgtk_kernels_v1.cuh"
 #include "tgtk_kernels_v2.cuh"
 #include "tgtk_kernels_v3.cuh"
+#include "tgtk_kernels_v5.cuh"
 
 using namespace tgtk;
 
@@ -86,6 +87,9 @@ struct tgtk_sim {
     bool host_sched = false;   // no stop criterion: parity baked into launches (see StepArgs)
     int sum_x0 = 0, sum_x1 = -1;     // planes counted in the volume (-1: all)
     int cur_par = 0, cur_slot = 0;   // launch-time values of StepArgs::par / slot
+    // fp32 rows are padded to an even pitch; for odd Z the pad element mirrors z = 0 (tgtk_kernels_v5.cuh).
+    // Only the v5 kernels keep the mirror current: anything else that writes state marks it stale.
+    bool pads_dirty = true;
     int minb = 0;          // FK_2c staged kernel: resident blocks per SM the register budget targets
     unsigned partials_cap = 0;
     std::vector<void *> snaps;     // one allocation per snapshot: nfields * n * elem
@@ -175,6 +179,16 @@ __global__ void unpack_kernel(const T *__restrict__ src, double *__restrict__ ds
         const int j = (int)(r % Y);
         const int i = (int)(r / Y);
         dst[q] = (double)src[i * sx + j * sy + k];
+    }
+}
+
+// odd-Z fp32 boxes: copy element z = 0 of every row into the pad element z = Z (tgtk_kernels_v5.cuh)
+template <typename T> __global__ void mirror_pad_kernel(T *__restrict__ arr, int X, int Y, int Z, int64_t sx, int64_t sy)
+{
+    const int64_t n = (int64_t)X * Y;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t d = (q / Y) * sx + (q % Y) * sy;
+        arr[d + Z] = arr[d];
     }
 }
 
@@ -282,10 +296,40 @@ template <typename T> static void fill_args(const tgtk_sim *s, StepArgs<T> &a)
 
 // variant 0 = auto = the staged kernels with two voxels per thread (v4), fastest for every model and
 // dtype measured on B200; 1, 2, 3 select the earlier families (cross-checks)
+static bool has_v5(const tgtk_sim *s)
+{
+    const int m = s->p.model;
+    return s->p.dtype == TGTK_F32 && (m == TGTK_MODEL_FK || m == TGTK_MODEL_FK_2C || m == TGTK_MODEL_DTI);
+}
+
+// 5 / 6 = the fp32 z-pair kernels with four / two voxels per thread (tgtk_kernels_v5.cuh); fp64 has no
+// such family and runs the two-voxel kernels (4) instead.  Auto (0): measured on B200 the
+// z-pair kernels win for FK_DTI (four arrays streamed per voxel, one through shared memory: 64-bit
+// accesses halve the load count) and lose for FK / FK_2c, whose tiles carry the coefficient as well and
+// pay for the scalar left / right reads with shared-memory bank conflicts.
 static int effective_variant(const tgtk_sim *s)
 {
-    if (s->variant != 0) return s->variant;
-    return 4;
+    if (s->variant == 0) return (has_v5(s) && s->p.model == TGTK_MODEL_DTI) ? 6 : 4;
+    if (s->variant >= 5) return has_v5(s) ? s->variant : 4;
+    return s->variant;
+}
+static bool zpair_variant(const tgtk_sim *s) { const int v = effective_variant(s); return v == 5 || v == 6; }
+
+// refresh the z = 0 mirrors in the pad column of the current state and of the static arrays
+static int refresh_pads(tgtk_sim *s)
+{
+    const tgtk_params &p = s->p;
+    s->pads_dirty = false;
+    if (s->sy == p.Z || p.dtype != TGTK_F32) return 0;
+    const int cur = s->t_enqueued & 1;
+    const int g = grid_1d((size_t)p.X * p.Y);
+    for (int f = 0; f < s->nfields; ++f)
+        mirror_pad_kernel<float><<<g, 256, 0, s->stream>>>((float *)s->state[cur][f], p.X, p.Y, p.Z, s->sx, s->sy);
+    for (int c = 0; c < s->ncoef; ++c)
+        mirror_pad_kernel<float><<<g, 256, 0, s->stream>>>((float *)s->coef[c], p.X, p.Y, p.Z, s->sx, s->sy);
+    CU(cudaGetLastError());
+    s->aux_launches += s->nfields + s->ncoef;
+    return 0;
 }
 
 // v4 launches go through cudaLaunchKernelEx so that host-scheduled steps can carry the programmatic
@@ -310,6 +354,29 @@ template <typename T> static cudaError_t launch_step(tgtk_sim *s)
 {
     StepArgs<T> a;
     fill_args(s, a);
+    if constexpr (sizeof(T) == 4) {
+        if (s->lx > 0 && effective_variant(s) == 5) {   // fp32: four voxels per thread
+            const int mb = s->minb ? s->minb : 4;
+            switch (s->p.model) {
+            case TGTK_MODEL_FK: return launch_v4(s, fk_step_v5<16, 8, 4>, a, s->lx);
+            case TGTK_MODEL_DTI: return launch_v4(s, dti_step_v5<16, 8, 4>, a, s->lx);
+            default:
+                if (mb >= 4) return launch_v4(s, fk2c_step_v5<16, 8, 4>, a, s->lx);
+                return launch_v4(s, fk2c_step_v5<16, 8, 3>, a, s->lx);
+            }
+        }
+        if (s->lx > 0 && effective_variant(s) == 6) {   // fp32: one z pair per thread
+            const int mb = s->minb ? s->minb : 6;
+            switch (s->p.model) {
+            case TGTK_MODEL_FK: return launch_v4(s, fk_step_v6<16, 8, 8>, a, s->lx);
+            case TGTK_MODEL_DTI: return launch_v4(s, dti_step_v6<16, 8, 8>, a, s->lx);
+            default:
+                if (mb >= 6) return launch_v4(s, fk2c_step_v6<16, 8, 6>, a, s->lx);
+                return launch_v4(s, fk2c_step_v6<16, 8, 4>, a, s->lx);
+            }
+        }
+    }
+    if (s->sy != s->p.Z) s->pads_dirty = true;   // no other kernel maintains the z = 0 mirror
     if (s->lx > 0 && effective_variant(s) == 4 && s->p.model == TGTK_MODEL_FK) {
         if (s->block.x == 16) return launch_v4(s, fk_step_v4<T, 16, 8, 8>, a, s->lx);
         else if (s->block.y == 4) return launch_v4(s, fk_step_v4<T, 32, 4, 8>, a, s->lx);
@@ -420,6 +487,20 @@ static void drop_graph(tgtk_sim *s)
     }
 }
 
+static const void *v5_kernel(int model, int minb)
+{
+    if (model == TGTK_MODEL_FK) return (const void *)fk_step_v5<16, 8, 4>;
+    if (model == TGTK_MODEL_DTI) return (const void *)dti_step_v5<16, 8, 4>;
+    return (minb == 0 || minb >= 4) ? (const void *)fk2c_step_v5<16, 8, 4> : (const void *)fk2c_step_v5<16, 8, 3>;
+}
+
+static const void *v6_kernel(int model, int minb)
+{
+    if (model == TGTK_MODEL_FK) return (const void *)fk_step_v6<16, 8, 8>;
+    if (model == TGTK_MODEL_DTI) return (const void *)dti_step_v6<16, 8, 8>;
+    return (minb == 0 || minb >= 6) ? (const void *)fk2c_step_v6<16, 8, 6> : (const void *)fk2c_step_v6<16, 8, 4>;
+}
+
 static const void *v4_kernel(int model, int dtype, int rows, int minb)
 {
     if (rows == 16) {   // 16-wide tiles
@@ -467,7 +548,9 @@ static int configure_launch(tgtk_sim *s)
             const double cost = padded / ((double)p.Z * p.Y) + 0.08 * (tz == 16) + 0.03 * (tz == 64);   // full-warp rows measure faster
             if (cost < best) { best = cost; best_tz = tz; }
         }
-        const bool two_rows = (variant == 4);   // *_step_v4: 32 x 8 or 32 x 16 voxel tile, two rows per thread
+        const bool four = (variant == 5);       // *_step_v5 (fp32): 32 x 16 voxel tile on 16 x 8 threads
+        const bool zp1 = (variant == 6);        // *_step_v6 (fp32): 32 x 8 voxel tile on 16 x 8 threads
+        const bool two_rows = (variant == 4) || four || zp1;   // *_step_v4: 32 x 8 or 32 x 16 voxel tile, two rows per thread
         // v4 tiles: 32(z) x 8(y) voxels on 32x4 threads, 16 x 16 voxels on 16x8 threads (narrow boxes waste
         // fewer lanes), or 32 x 16 voxels on 32x8 threads (TGTK_V4_THREADS=256)
         bool narrow = false;
@@ -476,18 +559,20 @@ static int configure_launch(tgtk_sim *s)
             const double w16 = (double)((p.Z + 15) / 16 * 16) * ((p.Y + 15) / 16 * 16);
             narrow = s->force_tz ? (s->force_tz == 16) : (w16 * (1.0 + s->narrow_penalty) < w32);
         }
-        const int v4rows = narrow ? 8 : ((s->v4_threads == 128) ? 4 : 8);          // thread rows; voxel rows = 2x
-        const int tz = two_rows ? (narrow ? 16 : 32) : best_tz, ty = two_rows ? 2 * v4rows : 256 / tz;
+        if (four || zp1) narrow = false;
+        const int v4rows = (narrow || four || zp1) ? 8 : ((s->v4_threads == 128) ? 4 : 8);          // thread rows; voxel rows = 2x
+        const int tz = two_rows ? (narrow ? 16 : 32) : best_tz, ty = zp1 ? 8 : two_rows ? 2 * v4rows : 256 / tz;   // voxels per tile
         const int tiles = ((p.Z + tz - 1) / tz) * ((p.Y + ty - 1) / ty);
         // Segment length: trade the tail of the last wave (blocks / resident slots not an
         // integer) against the two extra planes every segment loads to prime its pipeline.
         int per_sm = 2, sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
-        const void *fn = two_rows ? v4_kernel(p.model, p.dtype, narrow ? 16 : v4rows, s->minb)
+        const void *fn = four ? v5_kernel(p.model, s->minb) : zp1 ? v6_kernel(p.model, s->minb)
+                         : two_rows ? v4_kernel(p.model, p.dtype, narrow ? 16 : v4rows, s->minb)
                          : (variant >= 3)
                              ? ((p.dtype == TGTK_F64) ? v3_kernel<double>(p.model, tz == 32, s->pf == 1 ? 14 : s->minb) : v3_kernel<float>(p.model, tz == 32, s->pf == 1 ? 14 : s->minb))
                              : ((p.dtype == TGTK_F64) ? v2_kernel<double>(p.model) : v2_kernel<float>(p.model));
-        const int nthreads = two_rows ? tz * v4rows : 256;
+        const int nthreads = (four || zp1) ? 128 : two_rows ? tz * v4rows : 256;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, nthreads, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
         const double slots = (double)sms * per_sm;
         int best_lx = p.X;
@@ -500,7 +585,7 @@ static int configure_launch(tgtk_sim *s)
         }
         s->lx = best_lx;
         const int nseg = (p.X + s->lx - 1) / s->lx;
-        s->block = dim3(tz, two_rows ? v4rows : ty, 1);
+        s->block = dim3((four || zp1) ? 16 : tz, two_rows ? v4rows : ty, 1);
         s->grid = dim3((p.Z + tz - 1) / tz, (p.Y + ty - 1) / ty, nseg);
     } else {
         s->lx = 0;
@@ -710,8 +795,9 @@ int tgtk_sim_create_ex(tgtk_sim **out, const tgtk_params *params, int device, vo
     }
     s->n = (size_t)p.X * p.Y * p.Z;
     s->elem = (p.dtype == TGTK_F64) ? 8 : 4;
-    s->sy = p.Z;
-    s->sx = (int64_t)p.Y * p.Z;
+    // fp32 rows have an even pitch: every (row, even z) pair is 8-byte aligned for the v5 kernels
+    s->sy = p.Z + ((p.dtype == TGTK_F32) ? (p.Z & 1) : 0);
+    s->sx = (int64_t)p.Y * s->sy;
     s->nfields = (p.model == TGTK_MODEL_FK_2C || p.model == TGTK_MODEL_FK2C_COEF12) ? 3 : 1;
     switch (p.model) {
     case TGTK_MODEL_FK: s->ncoef = 1; break;
@@ -793,10 +879,11 @@ void tgtk_sim_destroy(tgtk_sim *s)
 int tgtk_sim_set_variant(tgtk_sim *s, int variant)
 {
     if (!s) return fail("tgtk_sim_set_variant", "null argument");
-    if (variant < 0 || variant > 4) return fail("tgtk_sim_set_variant", "variant must be 0 (auto) or 1..4");
+    if (variant < 0 || variant > 6) return fail("tgtk_sim_set_variant", "variant must be 0 (auto) or 1..6");
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(s->stream));
     s->variant = variant;
+    s->pads_dirty = true;
     return configure_launch(s);
 }
 
@@ -843,6 +930,7 @@ int tgtk_sim_upload(tgtk_sim *s, int field, const double *host, const int64_t st
         p.model != TGTK_MODEL_FK2C_COEF12 && p.model != TGTK_MODEL_DTI_FULL)
         return fail("tgtk_sim_upload", "coefficient arrays of this model are built by tgtk_sim_prepare");
     if (copy_host_stage(s, const_cast<double *>(host), strides, true)) return 1;
+    s->pads_dirty = true;
     if (p.dtype == TGTK_F64)
         pack_kernel<double><<<grid_1d(s->n), 256, 0, s->stream>>>(s->stage, (double *)dst, p.X, p.Y, p.Z, s->sx, s->sy);
     else
@@ -933,6 +1021,7 @@ int tgtk_sim_prepare(tgtk_sim *s)
         if (host_sched != s->host_sched) drop_graph(s);
         s->host_sched = host_sched;
     }
+    if (refresh_pads(s)) return 1;
     // keep the initial state so a finished loop can be rerun without another upload
     const size_t bytes = (size_t)p.X * s->sx * s->elem;
     const int cur = s->t_enqueued & 1;
@@ -969,6 +1058,7 @@ int tgtk_sim_run(tgtk_sim *s, int nsteps, const int32_t *record_steps, int nreco
     if (!s->prepared) return fail("tgtk_sim_run", "call tgtk_sim_prepare first");
     if (nsteps < 0) return fail("tgtk_sim_run", "negative step count");
     CU(cudaSetDevice(s->device));
+    if (s->pads_dirty && zpair_variant(s) && refresh_pads(s)) return 1;
     if (ensure_volumes(s, s->t_enqueued + nsteps)) return 1;
     const size_t bytes = (size_t)s->p.X * s->sx * s->elem;
     int r = 0;

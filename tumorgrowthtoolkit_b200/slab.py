@@ -130,7 +130,10 @@ class CudaSlabStepper:
         self.sim.set_sum_range(plan.halo, plan.halo + plan.n)
         self.fields = state_fields
         self.steps = 0
-        shape = (params.X, params.Y, params.Z)
+        # planes as flat rows of the library's plane pitch (fp32 rows are padded to an even length): the
+        # exchange only slices axis 0, and whole planes -- pad elements included -- are what must travel
+        _, pitches, _ = self.sim.device_ptr(state_fields[0])
+        shape = (params.X, int(pitches[0]))
         typestr = "<f8" if params.dtype == nat.F64 else "<f4"
         self.views = {(f, w): torch.as_tensor(_RawCuda(self.sim.buffer_ptr(f, w), shape, typestr), device=f"cuda:{device}")
                       for f in state_fields for w in (0, 1)}
