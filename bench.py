@@ -321,6 +321,7 @@ def main():
 
     # ---- device-resident arm -------------------------------------------------------------
     sim, out_fields = make_sim(pb, args.precision, device)
+    tuning = sim.tuning()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{device}")
     launches0 = sim.sync().kernel_launches
 
@@ -409,7 +410,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(pb["model"], args.precision), "peak_source": peak_src,
                          "algorithmic_bytes_per_voxel_update": bpu, "kernel_us": 1e3 * launch_ms,
-                         "kernel": {"fk2c": "fk2c_step", "fk": "fk_step", "dti": "coef_step"}[pb["model"]]},
+                         "kernel": {"fk2c": "fk2c_step", "fk": "fk_step", "dti": "dti_step"}[pb["model"]] + "_v%d" % tuning["variant"],
+                         "launch": tuning},
             "clocks": clocks.summary(),
             "wall_s_timed_region": wall_max, "final_volume": final_volume, "e2e_final_volume": e2e_vol,
         }

@@ -117,17 +117,23 @@ int tgtk_sim_create(tgtk_sim **out, const tgtk_params *params, int device, void 
 int tgtk_sim_create_ex(tgtk_sim **out, const tgtk_params *params, int device, void *stream, int flags);
 void tgtk_sim_destroy(tgtk_sim *sim);
 
-/* Kernel family: 0 (default) = auto, 3 = marching kernels staged through shared memory,
- * 2 = marching kernels reading neighbours through L1, 1 = baseline one-voxel-per-thread kernels
+/* Kernel family: 0 (default) = auto (the fastest measured for the model / dtype), 4 = marching kernels
+ * staged through shared memory with two voxels (rows y, y+1) per thread, 5 / 6 = fp32 only: z pairs with
+ * 64-bit accesses and packed f32x2 arithmetic, four / two voxels per thread, 3 = staged, one voxel per
+ * thread, 2 = marching kernels reading neighbours through L1, 1 = baseline one-voxel-per-thread kernels
  * kept as the in-device cross-check.  The environment variable TGTK_VARIANT sets the default.
  * All families compute the same operator. */
 int tgtk_sim_set_variant(tgtk_sim *sim, int variant);
+/* What the launch heuristics chose, for logs and benchmarks: out[0] kernel family in effect, out[1] planes
+ * per block segment, out[2] L2 prefetch distance in planes (0 = off), out[3] programmatic dependent launch
+ * (0/1), out[4..6] grid x, y, z, out[7] threads per block. */
+int tgtk_sim_get_tuning(tgtk_sim *sim, int32_t out[8]);
 
 /* Slab decomposition support.  set_sum_range: only planes [x0, x1) of axis 0 count towards the
  * volume (a rank's owned planes; its ghost planes are stepped but not summed).  buffer_ptr: device
  * address of ping-pong buffer `which` (0/1) of a state field, so halo planes can be exchanged in
- * place (NCCL send/recv on views of these buffers); the layout is dense C order (X,Y,Z) of the
- * simulation's dtype.  After n enqueued steps the current state is buffer n & 1. */
+ * place (NCCL send/recv on views of these buffers); the layout is C order (X,Y,Z) of the
+ * simulation's dtype with the pitches tgtk_sim_device_ptr reports (fp32 rows are padded to an even length).  After n enqueued steps the current state is buffer n & 1. */
 int tgtk_sim_set_sum_range(tgtk_sim *sim, int x0, int x1);
 int tgtk_sim_buffer_ptr(tgtk_sim *sim, int field, int which, unsigned long long *ptr);
 

@@ -85,6 +85,7 @@ def lib():
     i3 = ctypes.c_int32 * 3
     L.tgtk_sim_download_resampled.argtypes = [vp, ctypes.c_int, i3, i3, vp, i3]
     L.tgtk_sim_set_variant.argtypes = [vp, ctypes.c_int]
+    L.tgtk_sim_get_tuning.argtypes = [vp, ctypes.POINTER(ctypes.c_int32 * 8)]
     L.tgtk_sim_reset.argtypes = [vp]
     L.tgtk_sim_run.argtypes = [vp, ctypes.c_int, ip, ctypes.c_int]
     L.tgtk_sim_sync.argtypes = [vp, ctypes.POINTER(Status)]
@@ -177,6 +178,14 @@ class Sim:
 
     def set_variant(self, variant):
         _check(lib().tgtk_sim_set_variant(self._h, int(variant)))
+
+    def tuning(self):
+        """What the launch heuristics chose (after prepare): kernel family, planes per segment, L2 prefetch
+        distance, programmatic dependent launch, grid, threads per block."""
+        out = (ctypes.c_int32 * 8)()
+        _check(lib().tgtk_sim_get_tuning(self._h, ctypes.byref(out)))
+        return dict(variant=out[0], planes_per_segment=out[1], l2_prefetch_planes=out[2], pdl=bool(out[3]),
+                    grid=(out[4], out[5], out[6]), threads=out[7])
 
     def run_slab(self, comm, nsteps, halo, owned, prev, nxt):
         _check(lib().tgtk_sim_run_slab(self._h, comm, int(nsteps), int(halo), int(owned), int(prev), int(nxt)))

@@ -72,7 +72,9 @@ struct tgtk_sim {
                            // 2 planes when the arrays a step touches do not fit in L2, else off (measured:
                            // the requests only cost time when the working set is L2 resident)
     int l2_bytes = 0;      // cudaDevAttrL2CacheSize
-    int pdl = 1;           // host-scheduled v4 launches overlap their prologue with the previous step (TGTK_PDL=0: off)
+    int pdl = -1;          // host-scheduled launches overlap their prologue with the previous step's tail (TGTK_PDL):
+                           // 1 on, 0 off, -1 auto = on when the step's arrays fit in L2 (short launches, where the
+                           // launch gap matters; measured slightly negative for the long HBM-streaming launches)
     bool use_graph = true;
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // by parity of the first step
     cudaGraphExec_t slab_graph[2] = {nullptr, nullptr};   // tgtk_sim_run_slab: one block, by parity
@@ -85,6 +87,13 @@ struct tgtk_sim {
     int *peer_flags[2] = {nullptr, nullptr};
     void *peer_opened[2][7] = {};          // pointers to close with cudaIpcCloseMemHandle
     bool host_sched = false;   // no stop criterion: parity baked into launches (see StepArgs)
+    // A stop criterion is active: run host-scheduled all the same, chunk by chunk, behind a checkpoint of the
+    // state; chunk_finish_kernel runs the stop tests afterwards and a trip is replayed from the checkpoint up to
+    // the stopping step (fetch_ctrl).  TGTK_SPECULATE=0 selects the device-scheduled launches instead.
+    bool spec = false, replaying = false;
+    void *ckpt[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev2 = nullptr, ev3 = nullptr;   // around a replay
+    float replay_ms = 0.f;
     int sum_x0 = 0, sum_x1 = -1;     // planes counted in the volume (-1: all)
     int cur_par = 0, cur_slot = 0;   // launch-time values of StepArgs::par / slot
     // fp32 rows are padded to an even pitch; for odd Z the pad element mirrors z = 0 (tgtk_kernels_v5.cuh).
@@ -252,6 +261,23 @@ __global__ void prep_faces_kernel(const double *__restrict__ wm, const double *_
 // ------------------------------------------------------------------------------------------
 static inline int grid_1d(size_t n) { return (int)std::min<size_t>((n + 255) / 256, 148 * 16); }
 
+static bool exceeds_l2(const tgtk_sim *s)
+{
+    const tgtk_params &p = s->p;
+    const double touched = (double)(2 * s->nfields + s->ncoef) * (double)p.X * (double)s->sx * (double)s->elem;
+    return touched > 0.8 * (double)s->l2_bytes;
+}
+static int effective_l2pf(const tgtk_sim *s)
+{
+    const int l2pf = (s->l2pf < 0) ? (exceeds_l2(s) ? 2 : 0) : s->l2pf;
+    return (l2pf > 0 && l2pf < s->p.X) ? l2pf : 0;
+}
+static bool effective_pdl(const tgtk_sim *s)
+{
+    if (!s->host_sched && !s->spec) return false;
+    return (s->pdl < 0) ? !exceeds_l2(s) : (s->pdl != 0);
+}
+
 template <typename T> static void fill_args(const tgtk_sim *s, StepArgs<T> &a)
 {
     const tgtk_params &p = s->p;
@@ -281,17 +307,13 @@ template <typename T> static void fill_args(const tgtk_sim *s, StepArgs<T> &a)
     a.partials = s->partials;
     a.volumes = s->volumes;
     a.volumes_cap = s->volumes_cap;
-    a.host_sched = s->host_sched ? 1 : 0;
+    a.host_sched = (s->host_sched || s->spec) ? 1 : 0;
+    a.spec = (s->spec && !s->replaying) ? 1 : 0;
     a.par = s->cur_par;
     a.slot = s->cur_slot;
     a.sum_x0 = s->sum_x0;
     a.sum_x1 = (s->sum_x1 < 0) ? p.X : s->sum_x1;
-    int l2pf = s->l2pf;
-    if (l2pf < 0) {
-        const double touched = (double)(2 * s->nfields + s->ncoef) * (double)p.X * (double)s->sx * (double)s->elem;
-        l2pf = (touched > 0.8 * (double)s->l2_bytes) ? 2 : 0;
-    }
-    a.l2pf = (l2pf > 0 && l2pf < p.X) ? l2pf : 0;
+    a.l2pf = effective_l2pf(s);
 }
 
 // variant 0 = auto = the staged kernels with two voxels per thread (v4), fastest for every model and
@@ -346,7 +368,7 @@ template <typename... KA, typename... A> static cudaError_t launch_v4(tgtk_sim *
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = (s->pdl && s->host_sched && s->cur_slot > 0) ? 1 : 0;   // slot 0 follows a non-step node
+    cfg.numAttrs = (effective_pdl(s) && s->cur_slot > 0) ? 1 : 0;   // slot 0 follows a non-step node
     return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
@@ -636,7 +658,19 @@ static cudaError_t launch_chunk_finish(tgtk_sim *s, int count)
     const tgtk_params &p = s->p;
     ++s->aux_launches;
     chunk_finish_kernel<<<count, 256, 0, s->stream>>>(s->ctrl, s->partials, s->volumes, s->volumes_cap, s->nblocks, s->nfields,
-                                                   count, p.h[0] * p.h[1] * p.h[2], 1.0);
+                                                   count, p.h[0] * p.h[1] * p.h[2], 1.0, (s->spec && !s->replaying) ? 1 : 0,
+                                                   p.stopping_volume, p.small_volume);
+    return cudaGetLastError();
+}
+
+// speculative mode: copy the state held by ping-pong buffer `par` aside before a chunk starts
+static cudaError_t launch_checkpoint(tgtk_sim *s, int par)
+{
+    const size_t n8 = (size_t)s->p.X * s->sx * s->elem / 8;
+    ++s->aux_launches;
+    checkpoint_kernel<<<grid_1d(n8), 256, 0, s->stream>>>(s->ctrl, (const uint2 *)s->state[par][0], (const uint2 *)s->state[par][1],
+                                                       (const uint2 *)s->state[par][2], (uint2 *)s->ckpt[0], (uint2 *)s->ckpt[1],
+                                                       (uint2 *)s->ckpt[2], n8);
     return cudaGetLastError();
 }
 
@@ -645,9 +679,9 @@ static int build_graph(tgtk_sim *s, int par0)
 {
     cudaGraph_t graph = nullptr;
     CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
-    cudaError_t e = cudaSuccess;
+    cudaError_t e = s->spec ? launch_checkpoint(s, par0) : cudaSuccess;
     for (int i = 0; i < kGraphSteps && e == cudaSuccess; ++i) e = launch_one(s, (par0 + i) & 1, i);
-    if (e == cudaSuccess && s->host_sched) e = launch_chunk_finish(s, kGraphSteps);
+    if (e == cudaSuccess && (s->host_sched || s->spec)) e = launch_chunk_finish(s, kGraphSteps);
     cudaError_t e2 = cudaStreamEndCapture(s->stream, &graph);
     if (e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail("graph capture", cudaGetErrorString(e)); }
     if (e2 != cudaSuccess) return fail("cudaStreamEndCapture", cudaGetErrorString(e2));
@@ -860,6 +894,9 @@ void tgtk_sim_destroy(tgtk_sim *s)
     sim_free(s, s->stage);
     sim_free(s, s->resample_out);
     for (int f = 0; f < 3; ++f) sim_free(s, s->initial[f]);
+    for (int f = 0; f < 3; ++f) sim_free(s, s->ckpt[f]);
+    if (s->ev2) cudaEventDestroy(s->ev2);
+    if (s->ev3) cudaEventDestroy(s->ev3);
     sim_free(s, s->wm);
     sim_free(s, s->gm);
     sim_free(s, s->pc);
@@ -885,6 +922,19 @@ int tgtk_sim_set_variant(tgtk_sim *s, int variant)
     s->variant = variant;
     s->pads_dirty = true;
     return configure_launch(s);
+}
+
+int tgtk_sim_get_tuning(tgtk_sim *s, int32_t out[8])
+{
+    if (!s || !out) return fail("tgtk_sim_get_tuning", "null argument");
+    const bool marching = s->lx > 0;
+    out[0] = marching ? effective_variant(s) : 1;
+    out[1] = s->lx;
+    out[2] = (marching && effective_variant(s) >= 4) ? effective_l2pf(s) : 0;
+    out[3] = (marching && effective_variant(s) >= 4 && effective_pdl(s)) ? 1 : 0;
+    out[4] = (int32_t)s->grid.x; out[5] = (int32_t)s->grid.y; out[6] = (int32_t)s->grid.z;
+    out[7] = (int32_t)(s->block.x * s->block.y * s->block.z);
+    return 0;
 }
 
 int tgtk_sim_set_sum_range(tgtk_sim *s, int x0, int x1)
@@ -960,10 +1010,40 @@ static int current_buf(tgtk_sim *s, int *steps_run)
     return c.t & 1;
 }
 
+// Speculative mode: a stop test tripped inside a chunk whose later steps had already run.  Go back to the
+// checkpoint taken before the chunk and redo exactly the steps up to and including the stopping one
+// (FK.py:216-218: the state after the step whose volume tripped the test is the final state).
+static int replay_to_stop(tgtk_sim *s)
+{
+    const int t0 = s->ctrl_host->t, n = s->ctrl_host->replay;
+    if (n < 1 || n > kGraphSteps) return fail("replay", "inconsistent loop control");
+    const size_t bytes = (size_t)s->p.X * s->sx * s->elem;
+    CU(cudaEventRecord(s->ev2, s->stream));
+    for (int f = 0; f < s->nfields; ++f)
+        CU(cudaMemcpyAsync(s->state[t0 & 1][f], s->ckpt[f], bytes, cudaMemcpyDeviceToDevice, s->stream));
+    s->replaying = true;
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < n && e == cudaSuccess; ++i) e = launch_one(s, (t0 + i) & 1, i);
+    if (e == cudaSuccess) e = launch_chunk_finish(s, n);   // logs the volumes again, t = t0 + n, replay = 0
+    s->replaying = false;
+    if (e != cudaSuccess) return fail("replay launch", cudaGetErrorString(e));
+    CU(cudaEventRecord(s->ev3, s->stream));
+    s->launches += n;
+    CU(cudaMemcpyAsync(s->ctrl_host, s->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, s->ev2, s->ev3));
+    s->replay_ms += ms;
+    s->t_enqueued = s->ctrl_host->t;
+    s->pads_dirty = true;
+    return 0;
+}
+
 static int fetch_ctrl(tgtk_sim *s)
 {
     CU(cudaMemcpyAsync(s->ctrl_host, s->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
+    if (s->spec && s->ctrl_host->replay > 0) return replay_to_stop(s);
     return 0;
 }
 
@@ -1018,8 +1098,17 @@ int tgtk_sim_prepare(tgtk_sim *s)
         const bool want = std::isinf(p.stopping_volume) && p.stopping_volume > 0 && !(p.small_volume > 0);
         const char *v = getenv("TGTK_HOST_SCHED");
         const bool host_sched = want && !(v && atoi(v) == 0);
-        if (host_sched != s->host_sched) drop_graph(s);
+        const char *w = getenv("TGTK_SPECULATE");
+        const bool spec = !want && !(w && atoi(w) == 0);
+        if (host_sched != s->host_sched || spec != s->spec) drop_graph(s);
         s->host_sched = host_sched;
+        s->spec = spec;
+        if (spec) {
+            const size_t bytes = (size_t)p.X * s->sx * s->elem;
+            for (int f = 0; f < s->nfields; ++f)
+                if (!s->ckpt[f]) CU(sim_malloc(s, &s->ckpt[f], bytes));
+            if (!s->ev2) { CU(cudaEventCreate(&s->ev2)); CU(cudaEventCreate(&s->ev3)); }
+        }
     }
     if (refresh_pads(s)) return 1;
     // keep the initial state so a finished loop can be rerun without another upload
@@ -1070,6 +1159,7 @@ int tgtk_sim_run(tgtk_sim *s, int nsteps, const int32_t *record_steps, int nreco
     std::vector<void *> arenas(nsnap, nullptr);
     for (int i = 0; i < nsnap; ++i) CU(sim_malloc(s, (void **)(&arenas[i]), bytes * s->nfields));
     int used = 0;
+    s->replay_ms = 0.f;
     CU(cudaEventRecord(s->ev0, s->stream));
     int q = 0;
     while (q < nsteps) {
@@ -1088,9 +1178,9 @@ int tgtk_sim_run(tgtk_sim *s, int nsteps, const int32_t *record_steps, int nreco
         while (done < run_len) {
             // leftovers: plain launches, in host-scheduled mode closed by one chunk_finish
             const int n = std::min(run_len - done, kGraphSteps);
-            cudaError_t e = cudaSuccess;
+            cudaError_t e = s->spec ? launch_checkpoint(s, (t0 + done) & 1) : cudaSuccess;
             for (int i = 0; i < n && e == cudaSuccess; ++i) e = launch_one(s, (t0 + done + i) & 1, i);
-            if (e == cudaSuccess && s->host_sched) e = launch_chunk_finish(s, n);
+            if (e == cudaSuccess && (s->host_sched || s->spec)) e = launch_chunk_finish(s, n);
             if (e != cudaSuccess) return fail("step launch", cudaGetErrorString(e));
             done += n;
         }
@@ -1133,7 +1223,7 @@ int tgtk_sim_sync(tgtk_sim *s, tgtk_status *st)
         st->snapshots = valid;
         float ms = 0.f;
         if (s->timed) CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
-        st->loop_ms = ms;
+        st->loop_ms = ms + s->replay_ms;   // a speculative run's replay belongs to the loop
         st->kernel_launches = s->launches;
     }
     return 0;

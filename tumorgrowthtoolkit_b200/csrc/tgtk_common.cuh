@@ -20,6 +20,7 @@ struct Ctrl {
     int stop_step;    // step index that tripped the test, -1 if none
     unsigned ticket;  // last-block-done counter of the running launch
     double last_volume;
+    int replay;       // speculative mode: steps to redo from the checkpoint (state before step t) to reach the stop step
 };
 
 // Everything a step kernel needs; passed by value.
@@ -47,6 +48,9 @@ template <typename T> struct StepArgs {
     // chunk_finish_kernel reduces a whole chunk of steps later -- nothing on the step-to-step
     // critical path depends on a device-side read-modify-write.
     int host_sched, par, slot;
+    // host_sched launches of a run WITH a stop criterion (speculative mode, tgtk_api.cu): chunk_finish_kernel
+    // runs the stop tests for a whole chunk afterwards; once one has tripped every later launch is void
+    int spec;
     // planes [sum_x0, sum_x1) count towards the volume (slab mode: the owned planes, not the ghosts)
     int sum_x0, sum_x1;
     // marching kernels: planes ahead of the current one whose lines are requested into L2
@@ -118,7 +122,8 @@ template <typename T> __device__ __forceinline__ StepCtl step_begin(const StepAr
 {
     StepCtl c;
     if (a.host_sched) {
-        c.t = -1; c.par = a.par; c.stop = false;
+        // the flag is only ever written by a chunk_finish_kernel, which no step launch overlaps
+        c.t = -1; c.par = a.par; c.stop = a.spec && (*(volatile const int *)&a.ctrl->stop_reason != 0);
     } else {
         c.t = a.ctrl->t;
         c.par = c.t & 1;
@@ -288,11 +293,17 @@ __device__ __forceinline__ void step_end(const StepArgs<T> &a, const StepCtl &c,
 // Reduces the partial sums of `count` consecutive host-scheduled steps in a fixed order, logs the
 // volumes and advances the device step counter.  One block per step (ring slot = blockIdx.x); the
 // last block to finish (ticket) publishes the new step index, after every block has read the old.
+// spec != 0 (a run with a stop criterion, executed speculatively): the last block also runs the
+// reference's stop tests (FK.py:216-218, FK_DTI.py:199-206) over the chunk in step order.  On a trip
+// the step counter stays at the chunk's first step -- the state the checkpoint holds -- and `replay`
+// tells the host how many steps lead from there to the stopping step; later launches see the flag.
 __global__ void __launch_bounds__(256) chunk_finish_kernel(Ctrl *ctrl, const double *partials, double *volumes,
                                                            int volumes_cap, unsigned nblocks, int nfields, int count,
-                                                           double scale_p, double scale_n)
+                                                           double scale_p, double scale_n, int spec, double stop_volume,
+                                                           double small_volume)
 {
     __shared__ double red[2][8];
+    if (spec && *(volatile const int *)&ctrl->stop_reason != 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int j = blockIdx.x;
     const int t0 = ctrl->t;
@@ -312,12 +323,45 @@ __global__ void __launch_bounds__(256) chunk_finish_kernel(Ctrl *ctrl, const dou
         double vol = scale_p * a0;
         if (nfields > 1) vol += scale_n * a1;
         if (t0 + j < volumes_cap) volumes[t0 + j] = vol;
-        if (j == count - 1) ctrl->last_volume = vol;
+        if (!spec && j == count - 1) ctrl->last_volume = vol;
         __threadfence();
         if (atomicAdd(&ctrl->ticket, 1u) == (unsigned)count - 1) {
             ctrl->ticket = 0u;
-            ctrl->t = t0 + count;
+            if (!spec) {
+                ctrl->t = t0 + count;
+                ctrl->replay = 0;
+            } else {
+                __threadfence();
+                int trip = -1, reason = 0;
+                double v = 0.0;
+                for (int i = 0; i < count && t0 + i < volumes_cap; ++i) {
+                    v = __ldcg(&volumes[t0 + i]);
+                    if (v >= stop_volume) { trip = i; reason = 1; break; }
+                    if (v < small_volume) { trip = i; reason = 2; break; }
+                }
+                ctrl->last_volume = v;
+                if (trip >= 0) {
+                    ctrl->stop_step = t0 + trip;
+                    ctrl->replay = trip + 1;
+                    __threadfence();
+                    ctrl->stop_reason = reason;
+                } else {
+                    ctrl->t = t0 + count;
+                }
+            }
         }
+    }
+}
+
+// speculative mode: the state before a chunk, kept until the chunk's stop tests have passed
+__global__ void __launch_bounds__(256) checkpoint_kernel(const Ctrl *ctrl, const uint2 *s0, const uint2 *s1, const uint2 *s2,
+                                                         uint2 *d0, uint2 *d1, uint2 *d2, size_t n8)
+{
+    if (*(volatile const int *)&ctrl->stop_reason != 0) return;
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < n8; q += (size_t)gridDim.x * blockDim.x) {
+        d0[q] = s0[q];
+        if (s1) d1[q] = s1[q];
+        if (s2) d2[q] = s2[q];
     }
 }
 
