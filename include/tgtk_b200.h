@@ -236,6 +236,14 @@ int tgtk_sim_download_resampled(tgtk_sim *sim, int field, const int32_t lo[3], c
 int tgtk_resample_linear_host(int device, const double *in, const int64_t in_strides[3], const int32_t in_shape[3],
                               const int32_t lo[3], const int32_t virt_shape[3], double *out, const int32_t out_shape[3]);
 
+/* Batched 3x3 symmetric eigen-elongation on the device: tensors = n C-order 3x3 float64 tensors (host),
+ * out = n 3x3 float32 tensors (host), the dtype the reference returns.  Replaces
+ * tools.elongate_tensor_along_main_axis_torch (TumorGrowthToolkit/FK_DTI/tools.py:109-164; called from
+ * FK_DTI_Solver.solve, FK_DTI/FK_DTI.py:107-113, when diffusionEllipsoidScaling != 1): the largest
+ * eigenvalue is multiplied by scale_factor, the other two are shifted as the reference shifts them, the
+ * tensor is rebuilt.  Agreement with the reference's float32 LAPACK path is at float32 rounding level. */
+int tgtk_elongate_tensors_host(int device, const double *tensors, int64_t n, double scale_factor, float *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -322,8 +322,36 @@ def gen_atlas():
     print("atlas_res05.npz", os.path.getsize(os.path.join(GOLD, "atlas_res05.npz")))
 
 
+def elongate_inputs():
+    """Seeded (6,7,5,3,3) tensor field for the elongation (tools.py:109-164): SPD tensors with separated
+    eigenvalues, isotropic and axis-aligned degenerate tensors, zeros (background)."""
+    rng = np.random.default_rng(20261020)
+    shape = (6, 7, 5)
+    n = int(np.prod(shape))
+    q, _ = np.linalg.qr(rng.normal(size=(n, 3, 3)))
+    lam = np.sort(rng.uniform(0.2, 1.0, (n, 3)), axis=-1) * np.array([1.0, 1.6, 2.6]) * 1e-3
+    t = np.einsum("nij,nj,nkj->nik", q, lam, q)
+    t = 0.5 * (t + np.swapaxes(t, -1, -2))
+    special = [np.diag([1e-3] * 3), np.diag([1e-3, 2e-3, 2e-3]), np.diag([2e-3, 2e-3, 1e-3]), np.diag([2e-3, 1e-3, 2e-3]),
+               np.diag([3e-3, 1e-3, 2e-3]), np.zeros((3, 3)), np.diag([0.0, 0.0, 1.5e-3]), np.diag([7e-4, 7e-4, 0.0])]
+    for i, m in enumerate(special):
+        t[3 * i] = m
+    return t.reshape(shape + (3, 3))
+
+
+def gen_elongate():
+    """tools.elongate_tensor_along_main_axis_torch of the unmodified reference (float32 torch.linalg.eigh)."""
+    _, _, _, tools = import_reference()
+    t = elongate_inputs()
+    out = {"tensors": t}
+    for scale in (2.0, 0.6, 1.25):
+        out["scale_%g" % scale] = tools.elongate_tensor_along_main_axis_torch(t.copy(), scale)
+    np.savez_compressed(os.path.join(GOLD, "elongate.npz"), **out)
+    print("elongate.npz", os.path.getsize(os.path.join(GOLD, "elongate.npz")))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    groups = sys.argv[1:] or ["ops", "solve", "atlas"]
+    groups = sys.argv[1:] or ["ops", "solve", "atlas", "elongate"]
     for g in groups:
-        {"ops": gen_ops, "solve": gen_solve, "atlas": gen_atlas}[g]()
+        {"ops": gen_ops, "solve": gen_solve, "atlas": gen_atlas, "elongate": gen_elongate}[g]()

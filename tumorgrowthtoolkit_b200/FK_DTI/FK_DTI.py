@@ -54,7 +54,15 @@ class FK_DTI_Solver(FK_Solver):
 
         tensors = p["diffusionTensors"]
         if scaling != 1:                                                # FK_DTI.py:107-110
-            tensors = tools.elongate_tensor_along_main_axis_torch(tensors, scaling)
+            # 'torch' (default): the reference's own float32 CPU eigh, bit-identical preprocessing;
+            # 'cuda': csrc/tgtk_elongate.cuh, equal to float32 rounding and ~100x faster on a full volume
+            backend = p.get('elongation_backend', 'torch')
+            if backend == 'cuda':
+                tensors = tools.elongate_tensor_along_main_axis_cuda(tensors, scaling, device=self._device())
+            elif backend == 'torch':
+                tensors = tools.elongate_tensor_along_main_axis_torch(tensors, scaling)
+            else:
+                raise ValueError(f"elongation_backend must be 'torch' or 'cuda', got {backend!r}")
         rgb = tools.makeXYZ_rgb_from_tensor(tensors, exponent=exponent, linear=linear)
         full_tensor = bool(p.get('dti_full_tensor', False))
         if full_tensor and (exponent != 1 or linear != 0):

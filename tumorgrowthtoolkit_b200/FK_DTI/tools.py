@@ -21,8 +21,9 @@ def get_tensor_from_lower6(lower6):
 def elongate_tensor_along_main_axis_torch(tensor_arrayNP, scale_factor):
     """Scale the largest eigenvalue by `scale_factor`, shrink the other two so the trace is
     kept, rebuild the tensors; float32 torch.linalg.eigh on the CPU like the reference
-    (tools.py:109-164).  One-off preprocessing before the time loop; a batched 3x3 GPU eigh
-    is SURVEY.md 8(f) row F3 (cuSOLVER's syevBatched rejects this batch on sm_100)."""
+    (tools.py:109-164).  One-off preprocessing before the time loop.  This is the literal restatement
+    (bit-identical to the reference on the same torch build) that FK_DTI_Solver uses by default;
+    `elongate_tensor_along_main_axis_cuda` is the GPU kernel (params['elongation_backend'] = 'cuda')."""
     import torch
     with torch.no_grad():
         dev = "cpu"
@@ -40,6 +41,15 @@ def elongate_tensor_along_main_axis_torch(tensor_arrayNP, scale_factor):
         e_fin.scatter_(-1, imax, emax_scaled)
         out = v @ torch.diag_embed(e_fin) @ v.transpose(-2, -1)
         return out.cpu().numpy()
+
+
+def elongate_tensor_along_main_axis_cuda(tensor_arrayNP, scale_factor, device=0):
+    """The same elongation as a hand-written CUDA kernel (csrc/tgtk_elongate.cuh):
+    float64 closed-form top eigenpair per tensor instead of float32 LAPACK, float32 result like the
+    reference's.  Agrees with `elongate_tensor_along_main_axis_torch` to float32 rounding (1e-6 of the
+    largest entry), including the axis LAPACK picks for exactly diagonal degenerate tensors."""
+    from .. import _ops
+    return _ops.elongate_tensors(tensor_arrayNP, scale_factor, device=device)
 
 
 def makeXYZ_rgb_from_tensor(tensor, exponent=1, linear=0):

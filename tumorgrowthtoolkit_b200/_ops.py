@@ -130,3 +130,17 @@ def resample_linear(a, out_shape, lo=None, virt_shape=None, device=0):
                                      _vp(out), _I32x3(*out.shape))
     nat._check(rc)
     return out
+
+
+def elongate_tensors(tensors, scale_factor, device=0):
+    """tools.elongate_tensor_along_main_axis_torch (TumorGrowthToolkit/FK_DTI/tools.py:109-164) on the GPU:
+    (..., 3, 3) symmetric tensors -> float32 array of the same shape with the largest eigenvalue of every
+    tensor multiplied by `scale_factor` and the other two shifted as the reference shifts them."""
+    L = nat.lib()
+    t = np.ascontiguousarray(tensors, dtype=np.float64)
+    assert t.ndim >= 2 and t.shape[-2:] == (3, 3), "tensors must have shape (..., 3, 3)"
+    out = np.empty(t.shape, dtype=np.float32)
+    n = int(np.prod(t.shape[:-2], dtype=np.int64))
+    L.tgtk_elongate_tensors_host.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p]
+    nat._check(L.tgtk_elongate_tensors_host(int(device), t.ctypes.data, n, float(scale_factor), out.ctypes.data))
+    return out

@@ -16,6 +16,7 @@
 #include "tgtk_kernels_v2.cuh"
 #include "tgtk_kernels_v3.cuh"
 #include "tgtk_kernels_v5.cuh"
+#include "tgtk_elongate.cuh"
 
 using namespace tgtk;
 
@@ -417,6 +418,7 @@ template <typename T> static cudaError_t launch_step(tgtk_sim *s)
             if (mb >= 3) return launch_v4(s, fk2c_step_v4<T, 16, 8, 6>, a, s->lx);
             else return launch_v4(s, fk2c_step_v4<T, 16, 8, 4>, a, s->lx);
         } else if (s->block.y == 4) {
+            if (mb == 5) return launch_v4(s, fk2c_step_v4<T, 32, 4, 5>, a, s->lx);
             if (mb >= 3) return launch_v4(s, fk2c_step_v4<T, 32, 4, 6>, a, s->lx);
             else return launch_v4(s, fk2c_step_v4<T, 32, 4, 4>, a, s->lx);
         } else {
@@ -541,6 +543,7 @@ static const void *v4_kernel(int model, int dtype, int rows, int minb)
         return rows == 4 ? (const void *)dti_step_v4<float, 32, 4, 8> : (const void *)dti_step_v4<float, 32, 8, 4>;
     }
     if (minb == 0) minb = (dtype == TGTK_F64) ? 2 : 3;   // fp64: 120 registers, fp32: 76 (measured faster)
+    if (rows == 4 && minb == 5) return dtype == TGTK_F64 ? (const void *)fk2c_step_v4<double, 32, 4, 5> : (const void *)fk2c_step_v4<float, 32, 4, 5>;
     if (dtype == TGTK_F64) {
         if (rows == 4) return minb >= 3 ? (const void *)fk2c_step_v4<double, 32, 4, 6> : (const void *)fk2c_step_v4<double, 32, 4, 4>;
         return minb >= 3 ? (const void *)fk2c_step_v4<double, 32, 8, 3> : (const void *)fk2c_step_v4<double, 32, 8, 2>;
@@ -1400,6 +1403,39 @@ int tgtk_resample_linear_host(int device, const double *in, const int64_t in_str
         if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, nout * 8, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) rc = fail("resample", cudaGetErrorString(e));
+    }
+    if (din) cudaFreeAsync(din, st);
+    if (dout) cudaFreeAsync(dout, st);
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+int tgtk_elongate_tensors_host(int device, const double *tensors, int64_t n, double scale_factor, float *out)
+{
+    if (!tensors || !out) return fail("tgtk_elongate_tensors_host", "null argument");
+    if (n < 0) return fail("tgtk_elongate_tensors_host", "negative tensor count");
+    if (n == 0) return 0;
+    CU(cudaSetDevice(device));
+    cudaStream_t st = nullptr;
+    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    // chunks bound the device footprint (108 bytes per tensor) whatever the volume: 240x240x155 is 8.9 M tensors
+    const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 21);
+    double *din = nullptr;
+    float *dout = nullptr;
+    int rc = 0;
+    cudaError_t e = cudaMallocAsync((void **)&din, (size_t)chunk * 72, st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&dout, (size_t)chunk * 36, st);
+    if (e != cudaSuccess) rc = fail("cudaMalloc", cudaGetErrorString(e));
+    for (int64_t q = 0; q < n && !rc; q += chunk) {
+        const int64_t m = std::min(chunk, n - q);
+        e = cudaMemcpyAsync(din, tensors + q * 9, (size_t)m * 72, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) {
+            tgtk::elongate_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(din, dout, m, scale_factor);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out + q * 9, dout, (size_t)m * 36, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = fail("elongate", cudaGetErrorString(e));
     }
     if (din) cudaFreeAsync(din, st);
     if (dout) cudaFreeAsync(dout, st);

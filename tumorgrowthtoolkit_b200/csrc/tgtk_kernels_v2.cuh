@@ -106,6 +106,19 @@ template <typename T> __device__ __forceinline__ T heaviside50_fast(T s, T sigma
     return T(1) - fast_rcp(T(1) + fast_exp(arg));
 }
 
+// fp32: 1 - 1/(1 + 2^t), t = -50 log2(e) (s - sigma) capped so that 2^t stays finite, with the SFU's ex2 and
+// rcp (relative error 2^-22, far inside the fp32 mode's 1e-4 contract): 7 instructions instead of expf's range
+// handling plus the correctly rounded reciprocal's slow-path call.
+__device__ __forceinline__ float heaviside50_fast(float s, float sigma)
+{
+    const float c = 72.13475204444817f;   // 50 log2(e)
+    const float t = fminf(fmaf(s, -c, c * sigma), 115.0f);
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return 1.0f - r;
+}
+
 // All three kernels are software-pipelined along x: the own-column values of plane x+2 are
 // requested while plane x is computed (they are the loads that miss L1 and come from L2/HBM);
 // the in-plane neighbours of plane x are L1 hits issued at the top of the iteration.  The loop
