@@ -126,8 +126,9 @@ void tgtk_sim_destroy(tgtk_sim *sim);
 int tgtk_sim_set_variant(tgtk_sim *sim, int variant);
 /* What the launch heuristics chose, for logs and benchmarks: out[0] kernel family in effect, out[1] planes
  * per block segment, out[2] L2 prefetch distance in planes (0 = off), out[3] programmatic dependent launch
- * (0/1), out[4..6] grid x, y, z, out[7] threads per block. */
-int tgtk_sim_get_tuning(tgtk_sim *sim, int32_t out[8]);
+ * (0/1), out[4..6] grid x, y, z, out[7] threads per block, out[8] temporal blocking: time steps per
+ * launch (1 or 2), out[9] reserved (0). */
+int tgtk_sim_get_tuning(tgtk_sim *sim, int32_t out[10]);
 
 /* Slab decomposition support.  set_sum_range: only planes [x0, x1) of axis 0 count towards the
  * volume (a rank's owned planes; its ghost planes are stepped but not summed).  buffer_ptr: device

@@ -85,7 +85,7 @@ def lib():
     i3 = ctypes.c_int32 * 3
     L.tgtk_sim_download_resampled.argtypes = [vp, ctypes.c_int, i3, i3, vp, i3]
     L.tgtk_sim_set_variant.argtypes = [vp, ctypes.c_int]
-    L.tgtk_sim_get_tuning.argtypes = [vp, ctypes.POINTER(ctypes.c_int32 * 8)]
+    L.tgtk_sim_get_tuning.argtypes = [vp, ctypes.POINTER(ctypes.c_int32 * 10)]
     L.tgtk_sim_reset.argtypes = [vp]
     L.tgtk_sim_run.argtypes = [vp, ctypes.c_int, ip, ctypes.c_int]
     L.tgtk_sim_sync.argtypes = [vp, ctypes.POINTER(Status)]
@@ -182,10 +182,10 @@ class Sim:
     def tuning(self):
         """What the launch heuristics chose (after prepare): kernel family, planes per segment, L2 prefetch
         distance, programmatic dependent launch, grid, threads per block."""
-        out = (ctypes.c_int32 * 8)()
+        out = (ctypes.c_int32 * 10)()
         _check(lib().tgtk_sim_get_tuning(self._h, ctypes.byref(out)))
         return dict(variant=out[0], planes_per_segment=out[1], l2_prefetch_planes=out[2], pdl=bool(out[3]),
-                    grid=(out[4], out[5], out[6]), threads=out[7])
+                    grid=(out[4], out[5], out[6]), threads=out[7], steps_per_launch=out[8])
 
     def run_slab(self, comm, nsteps, halo, owned, prev, nxt):
         _check(lib().tgtk_sim_run_slab(self._h, comm, int(nsteps), int(halo), int(owned), int(prev), int(nxt)))

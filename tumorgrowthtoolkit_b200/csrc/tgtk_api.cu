@@ -16,6 +16,7 @@
 #include "tgtk_kernels_v2.cuh"
 #include "tgtk_kernels_v3.cuh"
 #include "tgtk_kernels_v5.cuh"
+#include "tgtk_kernels_tb.cuh"
 #include "tgtk_elongate.cuh"
 
 using namespace tgtk;
@@ -102,11 +103,20 @@ struct tgtk_sim {
     bool pads_dirty = true;
     int minb = 0;          // FK_2c staged kernel: resident blocks per SM the register budget targets
     unsigned partials_cap = 0;
+    // temporal blocking (tgtk_kernels_tb.cuh): two steps per launch where a kernel exists (FK_DTI) and the
+    // run is host-scheduled or speculative.  TGTK_TB: 1 on, 0 off, -1 auto (fp64 boxes of more than twice the L2)
+    int tb = -1;
+    int tb_rows = 18;      // thread rows of the two-step kernel's block: 18 (16 output rows, 576 threads) or 10 (8, 320)
+    dim3 tb_grid, tb_block;
+    int tb_lx = 0;
+    unsigned tb_nblocks = 0, ring_stride = 0, chunk_tb_mask = 0;
     std::vector<void *> snaps;     // one allocation per snapshot: nfields * n * elem
     std::vector<int> snap_steps;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     int64_t launches = 0;       // step-kernel launches (graph nodes included)
+    int graph_launches = kGraphSteps;   // step-kernel nodes of one captured chunk
+    int slab_block_launches = 0;        // ... of one captured slab block
     int64_t aux_launches = 0;   // chunk reductions and other helper kernels, as enqueued or captured
 };
 
@@ -306,6 +316,7 @@ template <typename T> static void fill_args(const tgtk_sim *s, StepArgs<T> &a)
     a.small_volume = p.small_volume;
     a.ctrl = s->ctrl;
     a.partials = s->partials;
+    a.ring_stride = s->ring_stride;
     a.volumes = s->volumes;
     a.volumes_cap = s->volumes_cap;
     a.host_sched = (s->host_sched || s->spec) ? 1 : 0;
@@ -619,12 +630,39 @@ static int configure_launch(tgtk_sim *s)
     }
     s->nblocks = s->grid.x * s->grid.y * s->grid.z;
     drop_graph(s);
-    if (s->nblocks > s->partials_cap) {
+    // two-step kernel geometry: 30 x (rows - 2) output voxels per 32 x rows thread block, x cut into segments like above
+    s->tb_nblocks = 0;
+    if (p.model == TGTK_MODEL_DTI && fits32) {
+        const int rows = (s->tb_rows == 10) ? 10 : 18, oy = rows - 2;
+        const int tiles = ((p.Z + 29) / 30) * ((p.Y + oy - 1) / oy);
+        int per_sm = 2, sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+        const void *fn = (p.dtype == TGTK_F64)
+                             ? (rows == 10 ? (const void *)dti_step2_tb<double, 10, 3> : (const void *)dti_step2_tb<double, 18, 2>)
+                             : (rows == 10 ? (const void *)dti_step2_tb<float, 10, 3> : (const void *)dti_step2_tb<float, 18, 2>);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 32 * rows, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+        const double slots = (double)sms * per_sm;
+        int best_lx = p.X;
+        double best_eff = -1.0;
+        for (int lx = 1; lx <= p.X; ++lx) {
+            const int ns = (p.X + lx - 1) / lx;
+            const double waves = tiles * (double)ns / slots;
+            const double eff = waves / std::ceil(waves) * (lx / (lx + 2.0)) * ((double)p.X / ((double)ns * lx));   // two extra planes per segment
+            if (eff > best_eff + 1e-9) { best_eff = eff; best_lx = lx; }
+        }
+        s->tb_lx = best_lx;
+        s->tb_block = dim3(32, rows, 1);
+        s->tb_grid = dim3((p.Z + 29) / 30, (p.Y + oy - 1) / oy, (p.X + best_lx - 1) / best_lx);
+        s->tb_nblocks = s->tb_grid.x * s->tb_grid.y * s->tb_grid.z;
+    }
+    const unsigned need = std::max(s->nblocks, s->tb_nblocks);
+    if (need > s->partials_cap) {
         if (s->partials) CU(sim_free(s, s->partials));
         s->partials = nullptr;
-        CU(sim_malloc(s, (void **)(&s->partials), sizeof(double) * 2 * s->nblocks * kGraphSteps));   // ring of kGraphSteps slots
-        s->partials_cap = s->nblocks;
+        CU(sim_malloc(s, (void **)(&s->partials), sizeof(double) * 2 * need * kGraphSteps));   // ring of kGraphSteps slots
+        s->partials_cap = need;
     }
+    s->ring_stride = 2 * s->partials_cap;
     return 0;
 }
 
@@ -656,13 +694,74 @@ static cudaError_t launch_one(tgtk_sim *s, int par, int slot)
     return (s->p.dtype == TGTK_F64) ? launch_step<double>(s) : launch_step<float>(s);
 }
 
+static bool tb_enabled(const tgtk_sim *s)
+{
+    if (s->tb_nblocks == 0 || !(s->host_sched || s->spec) || s->replaying) return false;
+    if (s->tb >= 0) return s->tb != 0;
+    // auto: measured on B200 the two-step kernel wins where the one-step kernel sits on the HBM
+    // roofline -- fp64 boxes well beyond L2 (+20 % at 28 M voxels) -- and is level or behind elsewhere
+    const tgtk_params &p = s->p;
+    const double touched = (double)(2 * s->nfields + s->ncoef) * (double)p.X * (double)s->sx * (double)s->elem;
+    return p.dtype == TGTK_F64 && touched > 2.0 * (double)s->l2_bytes;
+}
+
+// two steps in one launch: reads state[par], writes state[par ^ 1], partial sums into ring slots slot, slot + 1
+static cudaError_t launch_pair(tgtk_sim *s, int par, int slot)
+{
+    s->cur_par = par;
+    s->cur_slot = slot;
+    const dim3 g = s->grid, b = s->block;
+    s->grid = s->tb_grid;
+    s->block = s->tb_block;
+    cudaError_t e;
+    if (s->p.dtype == TGTK_F64) {
+        StepArgs<double> a;
+        fill_args(s, a);
+        e = (s->tb_rows == 10) ? launch_v4(s, dti_step2_tb<double, 10, 3>, a, s->tb_lx) : launch_v4(s, dti_step2_tb<double, 18, 2>, a, s->tb_lx);
+    } else {
+        StepArgs<float> a;
+        fill_args(s, a);
+        e = (s->tb_rows == 10) ? launch_v4(s, dti_step2_tb<float, 10, 3>, a, s->tb_lx) : launch_v4(s, dti_step2_tb<float, 18, 2>, a, s->tb_lx);
+    }
+    s->grid = g;
+    s->block = b;
+    if (s->sy != s->p.Z) s->pads_dirty = true;
+    return e;
+}
+
+// n consecutive steps of one chunk starting with ping-pong parity par0, ring slots 0..n-1.  With temporal
+// blocking an EVEN number of two-step launches comes first: each one writes the buffer the state did not
+// live in, so the two buffer pointers are swapped after it (state after t steps stays in state[t & 1]); an
+// even count leaves the pointers as they were, which is what captured graphs and the peers of a slab rely on.
+static cudaError_t launch_steps(tgtk_sim *s, int par0, int n)
+{
+    int i = 0;
+    cudaError_t e = cudaSuccess;
+    if (tb_enabled(s)) {
+        const int pairs = (n / 4) * 2;
+        for (int j = 0; j < pairs && e == cudaSuccess; ++j, i += 2) {
+            e = launch_pair(s, par0, i);
+            for (int f = 0; f < s->nfields; ++f) std::swap(s->state[0][f], s->state[1][f]);
+            s->chunk_tb_mask |= 3u << i;
+            ++s->launches;
+        }
+    }
+    for (; i < n && e == cudaSuccess; ++i) {
+        e = launch_one(s, (par0 + i) & 1, i);
+        ++s->launches;
+    }
+    return e;
+}
+
 static cudaError_t launch_chunk_finish(tgtk_sim *s, int count)
 {
     const tgtk_params &p = s->p;
     ++s->aux_launches;
     chunk_finish_kernel<<<count, 256, 0, s->stream>>>(s->ctrl, s->partials, s->volumes, s->volumes_cap, s->nblocks, s->nfields,
                                                    count, p.h[0] * p.h[1] * p.h[2], 1.0, (s->spec && !s->replaying) ? 1 : 0,
-                                                   p.stopping_volume, p.small_volume);
+                                                   p.stopping_volume, p.small_volume, s->ring_stride, s->tb_nblocks,
+                                                   s->chunk_tb_mask);
+    s->chunk_tb_mask = 0;
     return cudaGetLastError();
 }
 
@@ -683,7 +782,10 @@ static int build_graph(tgtk_sim *s, int par0)
     cudaGraph_t graph = nullptr;
     CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
     cudaError_t e = s->spec ? launch_checkpoint(s, par0) : cudaSuccess;
-    for (int i = 0; i < kGraphSteps && e == cudaSuccess; ++i) e = launch_one(s, (par0 + i) & 1, i);
+    const int64_t before = s->launches;
+    if (e == cudaSuccess) e = launch_steps(s, par0, kGraphSteps);
+    s->graph_launches = (int)(s->launches - before);
+    s->launches = before;                      // capture is not execution: tgtk_sim_run counts the replays
     if (e == cudaSuccess && (s->host_sched || s->spec)) e = launch_chunk_finish(s, kGraphSteps);
     cudaError_t e2 = cudaStreamEndCapture(s->stream, &graph);
     if (e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail("graph capture", cudaGetErrorString(e)); }
@@ -854,6 +956,8 @@ int tgtk_sim_create_ex(tgtk_sim **out, const tgtk_params *params, int device, vo
     if (const char *v = getenv("TGTK_TZ")) s->force_tz = atoi(v);
     if (const char *v = getenv("TGTK_L2PF")) s->l2pf = atoi(v);
     if (const char *v = getenv("TGTK_PDL")) s->pdl = atoi(v);
+    if (const char *v = getenv("TGTK_TB")) s->tb = atoi(v);
+    if (const char *v = getenv("TGTK_TB_ROWS")) s->tb_rows = atoi(v);
     if (cudaDeviceGetAttribute(&s->l2_bytes, cudaDevAttrL2CacheSize, s->device) != cudaSuccess) s->l2_bytes = 0;
     *out = s;  // from here on tgtk_sim_destroy cleans up on failure
     if (configure_launch(s)) return 1;
@@ -927,7 +1031,7 @@ int tgtk_sim_set_variant(tgtk_sim *s, int variant)
     return configure_launch(s);
 }
 
-int tgtk_sim_get_tuning(tgtk_sim *s, int32_t out[8])
+int tgtk_sim_get_tuning(tgtk_sim *s, int32_t out[10])
 {
     if (!s || !out) return fail("tgtk_sim_get_tuning", "null argument");
     const bool marching = s->lx > 0;
@@ -937,6 +1041,8 @@ int tgtk_sim_get_tuning(tgtk_sim *s, int32_t out[8])
     out[3] = (marching && effective_variant(s) >= 4 && effective_pdl(s)) ? 1 : 0;
     out[4] = (int32_t)s->grid.x; out[5] = (int32_t)s->grid.y; out[6] = (int32_t)s->grid.z;
     out[7] = (int32_t)(s->block.x * s->block.y * s->block.z);
+    out[8] = tb_enabled(s) ? 2 : 1;
+    out[9] = 0;
     return 0;
 }
 
@@ -1176,18 +1282,18 @@ int tgtk_sim_run(tgtk_sim *s, int nsteps, const int32_t *record_steps, int nreco
             const int par0 = (t0 + done) & 1;
             if (!s->graph_exec[par0] && build_graph(s, par0)) return 1;
             CU(cudaGraphLaunch(s->graph_exec[par0], s->stream));
+            s->launches += s->graph_launches;
             done += kGraphSteps;
         }
         while (done < run_len) {
             // leftovers: plain launches, in host-scheduled mode closed by one chunk_finish
             const int n = std::min(run_len - done, kGraphSteps);
             cudaError_t e = s->spec ? launch_checkpoint(s, (t0 + done) & 1) : cudaSuccess;
-            for (int i = 0; i < n && e == cudaSuccess; ++i) e = launch_one(s, (t0 + done + i) & 1, i);
+            if (e == cudaSuccess) e = launch_steps(s, (t0 + done) & 1, n);
             if (e == cudaSuccess && (s->host_sched || s->spec)) e = launch_chunk_finish(s, n);
             if (e != cudaSuccess) return fail("step launch", cudaGetErrorString(e));
             done += n;
         }
-        s->launches += run_len;
         s->t_enqueued += run_len;
         q += run_len;
         const int t = s->t_enqueued - 1;

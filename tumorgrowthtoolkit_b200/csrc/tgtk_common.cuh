@@ -38,7 +38,8 @@ template <typename T> struct StepArgs {
     double stop_volume;
     double small_volume;
     Ctrl *ctrl;
-    double *partials;      // [2][nblocks] per-block sums (field 0, field 1)
+    double *partials;      // [2][nblocks] per-block sums (field 0, field 1); host-scheduled: a ring of such slots
+    unsigned ring_stride;  // doubles per ring slot (fits the largest grid of the simulation's kernels)
     double *volumes;       // per-step volume log
     int volumes_cap;
     // Scheduling.  host_sched = 0: the step index and the stop flag live on the device (Ctrl)
@@ -276,7 +277,7 @@ __device__ __forceinline__ void finish_light(const StepArgs<T> &a, double s0, do
         v0 = warp_sum(v0);
         if (kFields > 1) v1 = warp_sum(v1);
         if (lane == 0) {
-            double *ring = a.partials + (size_t)a.slot * 2 * nblocks;
+            double *ring = a.partials + (size_t)a.slot * a.ring_stride;
             ring[bid] = v0;
             if (kFields > 1) ring[nblocks + bid] = v1;
         }
@@ -300,14 +301,16 @@ __device__ __forceinline__ void step_end(const StepArgs<T> &a, const StepCtl &c,
 __global__ void __launch_bounds__(256) chunk_finish_kernel(Ctrl *ctrl, const double *partials, double *volumes,
                                                            int volumes_cap, unsigned nblocks, int nfields, int count,
                                                            double scale_p, double scale_n, int spec, double stop_volume,
-                                                           double small_volume)
+                                                           double small_volume, unsigned ring_stride, unsigned nblocks_tb,
+                                                           unsigned tb_mask)
 {
     __shared__ double red[2][8];
     if (spec && *(volatile const int *)&ctrl->stop_reason != 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int j = blockIdx.x;
     const int t0 = ctrl->t;
-    const double *ring = partials + (size_t)j * 2 * nblocks;
+    const double *ring = partials + (size_t)j * ring_stride;
+    if ((tb_mask >> j) & 1u) nblocks = nblocks_tb;       // slot written by a two-step launch (its own grid)
     double v0 = 0.0, v1 = 0.0;
     for (unsigned i = tid; i < nblocks; i += 256) {
         v0 += ring[i];
