@@ -803,11 +803,6 @@ static void *field_ptr(tgtk_sim *s, int field, int which_buf)
     return nullptr;
 }
 
-static bool dense(const tgtk_sim *s, const int64_t st[3])
-{
-    return st[2] == 1 && st[1] == s->p.Z && st[0] == (int64_t)s->p.Y * s->p.Z;
-}
-
 // host (float64, strided) <-> dense float64 device buffer of shape (X,Y,Z)
 static int copy_host_dev(cudaStream_t stream, int X, int Y, int Z, double *dev, double *host, const int64_t st[3],
                          bool to_device)
