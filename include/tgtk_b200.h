@@ -229,6 +229,21 @@ int tgtk_faces_host(int device, int X, int Y, int Z, const double *wm, const int
 int tgtk_sim_download_resampled(tgtk_sim *sim, int field, const int32_t lo[3], const int32_t virt_shape[3], double *out,
                                 const int32_t out_shape[3]);
 
+/* Asynchronous patient outputs (synthetic_gens/generatePatient_FK_2c.py:141-155 does the
+ * same on the CPU after solve()).  Both calls only ENQUEUE on the simulation's stream -- restore_tumor + zoom(order=1)
+ * read straight from the state (bit-identical to tgtk_sim_download_resampled), device-to-host copy -- and return;
+ * `out` is valid after the next tgtk_sim_sync.  Pass buffers from tgtk_host_alloc (page-locked) so that the copies
+ * run at link speed and overlap other simulations' kernels.  tgtk_sim_segmentation_async evaluates
+ * create_segmentation_map (generatePatient_FK_2c.py:67-83) on the resampled P and N on the fly and returns labels
+ * 0 / 1 / 3 / 4 as uint8 (the reference's map is int64 with the same values). */
+int tgtk_sim_download_resampled_async(tgtk_sim *sim, int field, const int32_t lo[3], const int32_t virt_shape[3], double *out,
+                                      const int32_t out_shape[3]);
+int tgtk_sim_segmentation_async(tgtk_sim *sim, const int32_t lo[3], const int32_t virt_shape[3], const int32_t out_shape[3],
+                                double th_necro_n, double th_enhancing_p, double th_edema_p, uint8_t *out);
+/* Page-locked host memory for the buffers of the host-pointer entry points (NULL on failure). */
+void *tgtk_host_alloc(size_t bytes);
+void tgtk_host_free(void *ptr);
+
 /* scipy.ndimage.zoom(v, f, order=1) on the device (the resample of FK/FK.py:150-151,233-238).
  * `v` is a virtual float64 volume of shape virt_shape that is zero except for the box starting
  * at `lo` that holds `in` (restore_tumor, FK/FK.py:75-90, fused in; pass lo = 0 and

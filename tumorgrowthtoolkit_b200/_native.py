@@ -85,6 +85,13 @@ def lib():
     i3 = ctypes.c_int32 * 3
     L.tgtk_sim_download_resampled.argtypes = [vp, ctypes.c_int, i3, i3, vp, i3]
     L.tgtk_sim_set_variant.argtypes = [vp, ctypes.c_int]
+    i3p = ctypes.POINTER(ctypes.c_int32 * 3)
+    L.tgtk_sim_download_resampled_async.argtypes = [vp, ctypes.c_int, i3p, i3p, ctypes.c_void_p, i3p]
+    L.tgtk_sim_segmentation_async.argtypes = [vp, i3p, i3p, i3p, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_void_p]
+    L.tgtk_host_alloc.argtypes = [ctypes.c_size_t]
+    L.tgtk_host_alloc.restype = ctypes.c_void_p
+    L.tgtk_host_free.argtypes = [ctypes.c_void_p]
+    L.tgtk_host_free.restype = None
     L.tgtk_sim_get_tuning.argtypes = [vp, ctypes.POINTER(ctypes.c_int32 * 10)]
     L.tgtk_sim_reset.argtypes = [vp]
     L.tgtk_sim_run.argtypes = [vp, ctypes.c_int, ip, ctypes.c_int]
@@ -135,6 +142,34 @@ def make_params(model, dtype, shape, h, dt, rho=0.0, Dw=0.0, ratio=1.0, th_matte
     p.sigma_np, p.lambda_s = float(sigma_np), float(lambda_s)
     p.stopping_volume, p.small_volume = float(stopping_volume), float(small_volume)
     return p
+
+
+class _PinnedBlock:
+    """Owns one tgtk_host_alloc allocation; numpy arrays made by `pinned_empty` keep it alive through .base."""
+
+    def __init__(self, nbytes):
+        self.ptr = lib().tgtk_host_alloc(int(nbytes))
+        if not self.ptr:
+            raise NativeError("tgtk_host_alloc: " + lib().tgtk_last_error().decode())
+        self.nbytes = int(nbytes)
+        self.__array_interface__ = dict(shape=(max(self.nbytes, 1),), typestr="|u1", data=(int(self.ptr), False), version=3)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().tgtk_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array in page-locked host memory (tgtk_host_alloc): device-to-host copies into it run at link speed
+    and asynchronously.  The memory is released when the last view of the array is garbage collected."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    raw = np.asarray(_PinnedBlock(n))
+    return raw[:n].view(dtype).reshape(shape)
 
 
 class Sim:
@@ -246,6 +281,26 @@ class Sim:
         _check(lib().tgtk_sim_download_resampled(self._h, int(field), i3(*[int(v) for v in lo]),
                                                  i3(*[int(v) for v in virt_shape]), out.ctypes.data_as(ctypes.c_void_p),
                                                  i3(*out.shape)))
+        return out
+
+    def download_resampled_async(self, field, lo, virt_shape, out):
+        """Enqueue restore_tumor + zoom(order=1) + the copy into `out` (float64, C-contiguous, ideally from
+        pinned_empty) on the simulation's stream; `out` is valid after the next sync()."""
+        i3 = ctypes.c_int32 * 3
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.ndim == 3
+        _check(lib().tgtk_sim_download_resampled_async(self._h, int(field), ctypes.byref(i3(*[int(v) for v in lo])),
+                                                       ctypes.byref(i3(*[int(v) for v in virt_shape])), out.ctypes.data,
+                                                       ctypes.byref(i3(*out.shape))))
+        return out
+
+    def segmentation_async(self, lo, virt_shape, th_necro_n, th_enhancing_p, th_edema_p, out):
+        """Enqueue create_segmentation_map (generatePatient_FK_2c.py:67-83) of the full-resolution P and N, computed on
+        the device, into `out` (uint8 labels 0/1/3/4); valid after the next sync()."""
+        i3 = ctypes.c_int32 * 3
+        assert out.dtype == np.uint8 and out.flags.c_contiguous and out.ndim == 3
+        _check(lib().tgtk_sim_segmentation_async(self._h, ctypes.byref(i3(*[int(v) for v in lo])),
+                                                 ctypes.byref(i3(*[int(v) for v in virt_shape])), ctypes.byref(i3(*out.shape)),
+                                                 float(th_necro_n), float(th_enhancing_p), float(th_edema_p), out.ctypes.data))
         return out
 
     def snapshot(self, index, field, out=None):

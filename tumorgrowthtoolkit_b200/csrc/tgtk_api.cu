@@ -52,6 +52,9 @@ struct tgtk_sim {
     double *stage = nullptr;  // dense float64 staging for uploads / downloads
     double *resample_out = nullptr;   // device output of tgtk_sim_download_resampled
     size_t resample_cap = 0;
+    double *resample_async[3] = {nullptr, nullptr, nullptr};   // per-field outputs of the asynchronous downloads
+    uint8_t *seg_out = nullptr;
+    size_t resample_async_cap[3] = {0, 0, 0}, seg_cap = 0;
     void *initial[3] = {nullptr, nullptr, nullptr};  // state at prepare time (tgtk_sim_reset)
     double *wm = nullptr, *gm = nullptr, *pc = nullptr, *pn = nullptr;
     int faces_what = 0;  // tgtk_faces_host: 0 D_minus, 1 WM_tilda, 2 GM_tilda
@@ -93,6 +96,7 @@ struct tgtk_sim {
     // state; chunk_finish_kernel runs the stop tests afterwards and a trip is replayed from the checkpoint up to
     // the stopping step (fetch_ctrl).  TGTK_SPECULATE=0 selects the device-scheduled launches instead.
     bool spec = false, replaying = false;
+    bool ctrl_valid = false;   // the pinned mirror of Ctrl is current (nothing was enqueued since it was fetched)
     void *ckpt[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev2 = nullptr, ev3 = nullptr;   // around a replay
     float replay_ms = 0.f;
@@ -887,6 +891,68 @@ __global__ void resample_linear_kernel(const double *__restrict__ in, int IX, in
     }
 }
 
+// The same interpolation read straight from a pitched state array of the simulation's dtype (no staging):
+// the value at output voxel (i, j, k) of zoom(restore(field), order=1).  Same expressions as
+// resample_linear_kernel, so both paths return identical bits.
+struct ResampleGeom {
+    int IX, IY, IZ, lx, ly, lz, VX, VY, VZ, OX, OY, OZ;
+    int64_t sx, sy;
+    double fx, fy, fz;
+};
+
+template <typename T> __device__ __forceinline__ double resample_at(const T *__restrict__ in, const ResampleGeom &g, int i, int j, int k)
+{
+    const double xi = i * g.fx, yj = j * g.fy, zk = k * g.fz;
+    int i0 = (int)floor(xi), j0 = (int)floor(yj), k0 = (int)floor(zk);
+    i0 = min(i0, max(g.VX - 2, 0)); j0 = min(j0, max(g.VY - 2, 0)); k0 = min(k0, max(g.VZ - 2, 0));
+    const double tx = xi - i0, ty = yj - j0, tz = zk - k0;
+    double acc = 0.0;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int ii = min(i0 + a, g.VX - 1) - g.lx, jj = min(j0 + b, g.VY - 1) - g.ly, kk = min(k0 + c, g.VZ - 1) - g.lz;
+                const double w = (a ? tx : 1.0 - tx) * (b ? ty : 1.0 - ty) * (c ? tz : 1.0 - tz);
+                double v = 0.0;
+                if (ii >= 0 && ii < g.IX && jj >= 0 && jj < g.IY && kk >= 0 && kk < g.IZ) v = (double)in[(int64_t)ii * g.sx + (int64_t)jj * g.sy + kk];
+                acc += w * v;
+            }
+    return acc;
+}
+
+template <typename T> __global__ void resample_state_kernel(const T *__restrict__ in, ResampleGeom g, double *__restrict__ out)
+{
+    const int64_t n = (int64_t)g.OX * g.OY * g.OZ;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(q % g.OZ);
+        const int64_t r = q / g.OZ;
+        out[q] = resample_at(in, g, (int)(r / g.OY), (int)(r % g.OY), k);
+    }
+}
+
+// create_segmentation_map (synthetic_gens/generatePatient_FK_2c.py:67-83) of the full-resolution P and N,
+// evaluated on the fly: 3 edema (th_edema_p <= P < th_enhancing_p), 1 enhancing (P >= th_enhancing_p),
+// 4 necrotic (N > th_necro_n, wins), 0 elsewhere.
+template <typename T>
+__global__ void segmentation_kernel(const T *__restrict__ P, const T *__restrict__ N, ResampleGeom g, double th_necro_n,
+                                    double th_enhancing_p, double th_edema_p, uint8_t *__restrict__ out)
+{
+    const int64_t n = (int64_t)g.OX * g.OY * g.OZ;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(q % g.OZ);
+        const int64_t r = q / g.OZ;
+        const int j = (int)(r % g.OY), i = (int)(r / g.OY);
+        const double p = resample_at(P, g, i, j, k), nn = resample_at(N, g, i, j, k);
+        uint8_t lab = 0;
+        if (p >= th_edema_p && p < th_enhancing_p) lab = 3;
+        if (p >= th_enhancing_p) lab = 1;
+        if (nn > th_necro_n) lab = 4;
+        out[q] = lab;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 extern "C" {
 
@@ -995,6 +1061,8 @@ void tgtk_sim_destroy(tgtk_sim *s)
     for (void *q : s->snaps) sim_free(s, q);
     sim_free(s, s->stage);
     sim_free(s, s->resample_out);
+    for (int f = 0; f < 3; ++f) sim_free(s, s->resample_async[f]);
+    sim_free(s, s->seg_out);
     for (int f = 0; f < 3; ++f) sim_free(s, s->initial[f]);
     for (int f = 0; f < 3; ++f) sim_free(s, s->ckpt[f]);
     if (s->ev2) cudaEventDestroy(s->ev2);
@@ -1147,7 +1215,8 @@ static int fetch_ctrl(tgtk_sim *s)
 {
     CU(cudaMemcpyAsync(s->ctrl_host, s->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
-    if (s->spec && s->ctrl_host->replay > 0) return replay_to_stop(s);
+    if (s->spec && s->ctrl_host->replay > 0 && replay_to_stop(s)) return 1;
+    s->ctrl_valid = true;
     return 0;
 }
 
@@ -1235,6 +1304,7 @@ int tgtk_sim_reset(tgtk_sim *s)
     for (int f = 0; f < s->nfields; ++f)
         CU(cudaMemcpyAsync(s->state[0][f], s->initial[f], bytes, cudaMemcpyDeviceToDevice, s->stream));
     CU(cudaStreamSynchronize(s->stream));   // ctrl_host is about to be rewritten
+    s->ctrl_valid = false;
     Ctrl init = {0, 0, -1, 0u, 0.0};
     *s->ctrl_host = init;
     CU(cudaMemcpyAsync(s->ctrl, s->ctrl_host, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
@@ -1253,6 +1323,7 @@ int tgtk_sim_run(tgtk_sim *s, int nsteps, const int32_t *record_steps, int nreco
     CU(cudaSetDevice(s->device));
     if (s->pads_dirty && zpair_variant(s) && refresh_pads(s)) return 1;
     if (ensure_volumes(s, s->t_enqueued + nsteps)) return 1;
+    s->ctrl_valid = false;
     const size_t bytes = (size_t)s->p.X * s->sx * s->elem;
     int r = 0;
     while (r < nrecord && record_steps[r] < s->t_enqueued) ++r;
@@ -1475,6 +1546,94 @@ int tgtk_sim_download_resampled(tgtk_sim *s, int field, const int32_t lo[3], con
     CU(cudaMemcpyAsync(out, s->resample_out, nout * 8, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     return 0;
+}
+
+static int resample_geom(tgtk_sim *s, const char *who, const int32_t lo[3], const int32_t virt_shape[3], const int32_t out_shape[3],
+                         ResampleGeom &g)
+{
+    const tgtk_params &p = s->p;
+    const int in_shape[3] = {p.X, p.Y, p.Z};
+    for (int d = 0; d < 3; ++d)
+        if (virt_shape[d] < 1 || out_shape[d] < 1 || lo[d] < 0 || lo[d] + in_shape[d] > virt_shape[d]) return fail(who, "bad shape or box");
+    g.IX = p.X; g.IY = p.Y; g.IZ = p.Z;
+    g.lx = lo[0]; g.ly = lo[1]; g.lz = lo[2];
+    g.VX = virt_shape[0]; g.VY = virt_shape[1]; g.VZ = virt_shape[2];
+    g.OX = out_shape[0]; g.OY = out_shape[1]; g.OZ = out_shape[2];
+    g.sx = s->sx; g.sy = s->sy;
+    g.fx = (g.OX > 1) ? (double)(g.VX - 1) / (double)(g.OX - 1) : 0.0;
+    g.fy = (g.OY > 1) ? (double)(g.VY - 1) / (double)(g.OY - 1) : 0.0;
+    g.fz = (g.OZ > 1) ? (double)(g.VZ - 1) / (double)(g.OZ - 1) : 0.0;
+    return 0;
+}
+
+int tgtk_sim_download_resampled_async(tgtk_sim *s, int field, const int32_t lo[3], const int32_t virt_shape[3], double *out,
+                                      const int32_t out_shape[3])
+{
+    if (!s || !lo || !virt_shape || !out || !out_shape) return fail("tgtk_sim_download_resampled_async", "null argument");
+    if (field < 0 || field >= s->nfields) return fail("tgtk_sim_download_resampled_async", "not a state field of this model");
+    ResampleGeom g;
+    if (resample_geom(s, "tgtk_sim_download_resampled_async", lo, virt_shape, out_shape, g)) return 1;
+    CU(cudaSetDevice(s->device));
+    if (!s->ctrl_valid && fetch_ctrl(s)) return 1;   // the loop is over: which buffer holds the state, replay of a tripped stop
+    const void *src = s->state[current_buf(s, nullptr)][field];
+    const size_t nout = (size_t)g.OX * g.OY * g.OZ;
+    if (nout > s->resample_async_cap[field]) {
+        if (s->resample_async[field]) CU(sim_free(s, s->resample_async[field]));
+        s->resample_async[field] = nullptr;
+        s->resample_async_cap[field] = 0;
+        CU(sim_malloc(s, (void **)(&s->resample_async[field]), nout * 8));
+        s->resample_async_cap[field] = nout;
+    }
+    if (s->p.dtype == TGTK_F64) resample_state_kernel<double><<<grid_1d(nout), 256, 0, s->stream>>>((const double *)src, g, s->resample_async[field]);
+    else resample_state_kernel<float><<<grid_1d(nout), 256, 0, s->stream>>>((const float *)src, g, s->resample_async[field]);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, s->resample_async[field], nout * 8, cudaMemcpyDeviceToHost, s->stream));
+    return 0;
+}
+
+int tgtk_sim_segmentation_async(tgtk_sim *s, const int32_t lo[3], const int32_t virt_shape[3], const int32_t out_shape[3],
+                                double th_necro_n, double th_enhancing_p, double th_edema_p, uint8_t *out)
+{
+    if (!s || !lo || !virt_shape || !out || !out_shape) return fail("tgtk_sim_segmentation_async", "null argument");
+    if (s->p.model != TGTK_MODEL_FK_2C && s->p.model != TGTK_MODEL_FK2C_COEF12)
+        return fail("tgtk_sim_segmentation_async", "the segmentation map needs the P and N fields of FK_2c");
+    ResampleGeom g;
+    if (resample_geom(s, "tgtk_sim_segmentation_async", lo, virt_shape, out_shape, g)) return 1;
+    CU(cudaSetDevice(s->device));
+    if (!s->ctrl_valid && fetch_ctrl(s)) return 1;
+    const int cur = current_buf(s, nullptr);
+    const size_t nout = (size_t)g.OX * g.OY * g.OZ;
+    if (nout > s->seg_cap) {
+        if (s->seg_out) CU(sim_free(s, s->seg_out));
+        s->seg_out = nullptr;
+        s->seg_cap = 0;
+        CU(sim_malloc(s, (void **)(&s->seg_out), nout));
+        s->seg_cap = nout;
+    }
+    if (s->p.dtype == TGTK_F64)
+        segmentation_kernel<double><<<grid_1d(nout), 256, 0, s->stream>>>((const double *)s->state[cur][0], (const double *)s->state[cur][1], g,
+                                                                        th_necro_n, th_enhancing_p, th_edema_p, s->seg_out);
+    else
+        segmentation_kernel<float><<<grid_1d(nout), 256, 0, s->stream>>>((const float *)s->state[cur][0], (const float *)s->state[cur][1], g,
+                                                                       th_necro_n, th_enhancing_p, th_edema_p, s->seg_out);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, s->seg_out, nout, cudaMemcpyDeviceToHost, s->stream));
+    return 0;
+}
+
+void *tgtk_host_alloc(size_t bytes)
+{
+    void *q = nullptr;
+    if (cudaMallocHost(&q, bytes ? bytes : 8) != cudaSuccess) {
+        fail("tgtk_host_alloc", "cudaMallocHost failed");
+        return nullptr;
+    }
+    return q;
+}
+
+void tgtk_host_free(void *q)
+{
+    if (q) cudaFreeHost(q);
 }
 
 int tgtk_resample_linear_host(int device, const double *in, const int64_t in_strides[3], const int32_t in_shape[3],

@@ -94,6 +94,13 @@ class EnsembleRunner:
         self.S0 = np.ascontiguousarray(_host.crop(np.where(self.wm_lo + self.gm_lo >= th_matter, 1.0, 0.0), self.box))
         self.N0 = np.zeros_like(self.S0)
         self.voxels = int(self.cw.size)
+        # page-locked copies of what every patient uploads, and a ring of page-locked output sets: the device-to-host
+        # copies of one patient's full-resolution P, N, S and label map then overlap the other patients' kernels
+        for name in ("cw", "cg", "S0", "N0"):
+            pin = nat.pinned_empty(getattr(self, name).shape)
+            pin[...] = getattr(self, name)
+            setattr(self, name, pin)
+        self._outs, self._next_out = [], 0
 
     def _start(self, p):
         grid = _host.LowResGrid(self.gm_lo.shape, self.full_shape, self.res, *self.spacing,
@@ -116,19 +123,34 @@ class EnsembleRunner:
         sim.run(nsteps)          # asynchronous: the steps of several patients overlap on the GPU
         return dict(sim=sim, grid=grid, nsteps=nsteps, params=p)
 
-    def _finish(self, job):
+    def _output_set(self, shape):
+        """The next page-locked output set (P, N, S float64 + uint8 labels) of a ring of `concurrency + 1`."""
+        if not self._outs:      # page-locking is slow (~0.1 s per set): all sets at the first patient, none later
+            self._outs = [{k: nat.pinned_empty(shape) for k in "PNS"} | {"seg": nat.pinned_empty(shape, np.uint8)}
+                          for _ in range(self.concurrency + 1)]
+        self._next_out = (self._next_out + 1) % len(self._outs)
+        return self._outs[self._next_out]
+
+    def _finish(self, job, copy=True):
         sim, grid, p = job['sim'], job['grid'], job['params']
+        th = (p.get('th_necro_n', 0.12), p.get('th_enhancing_p', 0.4), p.get('th_edema_p', 0.15))
         st = sim.sync()
         assert st.steps_run == job['nsteps']
-        out = {}
-        for name, f in (('P', nat.FIELD_P), ('N', nat.FIELD_N), ('S', nat.FIELD_S)):
-            if self.full_resolution:
-                out[name] = sim.download_resampled(f, self.box[0], grid.shape, grid.full_shape)
-            else:
-                out[name] = sim.download(f)
+        if self.full_resolution:
+            # restore + zoom(order=1) of P, N, S and the label map (generatePatient_FK_2c.py:67-83,141-155) on the
+            # device, four asynchronous copies into page-locked memory, one wait
+            pin = self._output_set(grid.full_shape)
+            for name, f in (('P', nat.FIELD_P), ('N', nat.FIELD_N), ('S', nat.FIELD_S)):
+                sim.download_resampled_async(f, self.box[0], grid.shape, pin[name])
+            sim.segmentation_async(self.box[0], grid.shape, *th, pin['seg'])
+            sim.sync()
+            # results handed out are the caller's own: copy out of the ring unless they are dropped right away
+            out = {k: (pin[k].copy() if copy else pin[k]) for k in "PNS"}
+            seg = pin['seg'].copy() if copy else pin['seg']
+        else:
+            out = {name: sim.download(f) for name, f in (('P', nat.FIELD_P), ('N', nat.FIELD_N), ('S', nat.FIELD_S))}
+            seg = create_segmentation_map(out['P'], out['N'], *th)
         sim.close()
-        seg = create_segmentation_map(out['P'], out['N'], p.get('th_necro_n', 0.12), p.get('th_enhancing_p', 0.4),
-                                      p.get('th_edema_p', 0.15))
         return dict(final_state=out, segmentation=seg, final_volume=float(st.last_volume), steps=job['nsteps'],
                     loop_ms=float(st.loop_ms), params=p)
 
@@ -142,11 +164,11 @@ class EnsembleRunner:
             inflight.append((i, self._start(p)))
             if len(inflight) >= self.concurrency:
                 j, job = inflight.pop(0)
-                r = self._finish(job)
+                r = self._finish(job, copy=keep_results)
                 updates += r['steps'] * self.voxels
                 results[j] = r if keep_results else dict(final_volume=r['final_volume'], steps=r['steps'])
         for j, job in inflight:
-            r = self._finish(job)
+            r = self._finish(job, copy=keep_results)
             updates += r['steps'] * self.voxels
             results[j] = r if keep_results else dict(final_volume=r['final_volume'], steps=r['steps'])
         wall = time.perf_counter() - t0
