@@ -8,8 +8,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from tumorgrowthtoolkit_b200 import _native as nat
 
-WORDS = {"fk": 4, "dti": 5, "2c": 8}
-MODELS = {"fk": nat.MODEL_FK, "2c": nat.MODEL_FK_2C, "dti": nat.MODEL_DTI}
+WORDS = {"fk": 4, "dti": 5, "2c": 8, "dtifull": 8}
+MODELS = {"fk": nat.MODEL_FK, "2c": nat.MODEL_FK_2C, "dti": nat.MODEL_DTI, "dtifull": nat.MODEL_DTI_FULL}
 
 
 def peak_gbs():
@@ -29,9 +29,12 @@ def run(model, dtype, shape, nsteps):
         kw.update(th_necro=0.9, Ds=1.3, lambda_np=0.35, sigma_np=0.5, lambda_s=0.05)
     p = nat.make_params(MODELS[model], dtype, shape, (1, 1, 1), 0.01, **kw)
     with nat.Sim(p) as sim:
-        if model == "dti":
+        if model in ("dti", "dtifull"):
             for c in range(3):
                 sim.upload(nat.FIELD_COEF0 + c, rng.uniform(0.1, 1.0, shape))
+            if model == "dtifull":
+                for c in range(3, 6):
+                    sim.upload(nat.FIELD_COEF0 + c, rng.uniform(-0.05, 0.05, shape))
         else:
             sim.upload(nat.FIELD_WM, wm); sim.upload(nat.FIELD_GM, gm)
         sim.upload(nat.FIELD_U, u0)

@@ -442,6 +442,8 @@ template <typename T> static cudaError_t launch_step(tgtk_sim *s)
         }
         return cudaGetLastError();
     }
+    if (s->lx > 0 && s->p.model == TGTK_MODEL_DTI_FULL)   // 19-point stencil, four-plane shared-memory window
+        return launch_v4(s, dti_full_step_v3<T, 32, 8>, a, s->lx);
     if (s->lx > 0 && effective_variant(s) >= 3) {   // shared-memory staged marching kernels
         const bool wide = (s->block.x == 32);
         switch (s->p.model) {
@@ -627,6 +629,25 @@ static int configure_launch(tgtk_sim *s)
         const int nseg = (p.X + s->lx - 1) / s->lx;
         s->block = dim3((four || zp1) ? 16 : tz, two_rows ? v4rows : ty, 1);
         s->grid = dim3((p.Z + tz - 1) / tz, (p.Y + ty - 1) / ty, nseg);
+    } else if (p.model == TGTK_MODEL_DTI_FULL && variant >= 3 && fits32) {
+        // dti_full_step_v3: 32 x 8 tile, x cut into segments so that the grid is a whole number of waves
+        const int tiles = ((p.Z + 31) / 32) * ((p.Y + 7) / 8);
+        int per_sm = 2, sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+        const void *fn = (p.dtype == TGTK_F64) ? (const void *)dti_full_step_v3<double, 32, 8> : (const void *)dti_full_step_v3<float, 32, 8>;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+        const double slots = (double)sms * per_sm;
+        int best_lx = p.X;
+        double best_eff = -1.0;
+        for (int lx = 1; lx <= p.X; ++lx) {
+            const int ns = (p.X + lx - 1) / lx;
+            const double waves = tiles * (double)ns / slots;
+            const double eff = waves / std::ceil(waves) * (lx / (lx + 2.0)) * ((double)p.X / ((double)ns * lx));
+            if (eff > best_eff + 1e-9) { best_eff = eff; best_lx = lx; }
+        }
+        s->lx = best_lx;
+        s->block = dim3(32, 8, 1);
+        s->grid = dim3((p.Z + 31) / 32, (p.Y + 7) / 8, (p.X + best_lx - 1) / best_lx);
     } else {
         s->lx = 0;
         s->block = dim3(32, 4, 2);

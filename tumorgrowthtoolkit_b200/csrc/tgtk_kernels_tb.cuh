@@ -153,3 +153,98 @@ __global__ void __launch_bounds__(32 * TYT, MINB) dti_step2_tb(const StepArgs<T>
 }
 
 }  // namespace tgtk
+
+// =====================================================================================================
+// Full-tensor FK_DTI (19-point stencil, the opt-in mode of dti_full_step_v1) as a staged marching kernel.
+// The mixed-derivative terms read the four in-plane diagonals of plane x and the y/z neighbours of planes
+// x-1 and x+1, so the block keeps a rolling window of FOUR shared-memory planes (tile + a complete ring,
+// corners included): three are read while the fourth is being published for the next plane -- one barrier
+// per plane, no register copy of the neighbours.  The own voxel's u and six tensor components of plane x+1
+// are requested one plane ahead.  Expressions and their order are dti_full_step_v1's: bitwise equal to it.
+// =====================================================================================================
+namespace tgtk {
+
+template <typename T, int TZ, int TY>
+__global__ void __launch_bounds__(TZ *TY) dti_full_step_v3(const StepArgs<T> a, const int lx)
+{
+    using R = Rn<T>;
+    constexpr int RS = TZ + 2, PL = (TY + 2) * RS, NRING = 2 * RS + 2 * TY;
+    __shared__ T tile[4][PL];
+    const StepCtl sc = step_begin(a);
+    if (sc.stop) return;
+    const T *__restrict__ u = a.buf[sc.par][0];
+    T *__restrict__ out = a.buf[sc.par ^ 1][0];
+    const int tz = threadIdx.x, ty = threadIdx.y, tid = ty * TZ + tz;
+    const int z0 = blockIdx.x * TZ, y0 = blockIdx.y * TY;
+    const bool valid = (z0 + tz < a.Z) && (y0 + ty < a.Y);
+    const int x0 = blockIdx.z * lx, x1 = min(x0 + lx, a.X);
+    const uint32_t sx = (uint32_t)a.sx, sy = (uint32_t)a.sy;
+    const uint32_t col = (uint32_t)wrap_coord(y0 + ty, a.Y) * sy + (uint32_t)wrap_coord(z0 + tz, a.Z);
+    // ring with corners: RS above, RS below, TY left, TY right
+    const bool ring = tid < NRING;
+    int hr = 1, hc = 1;
+    if (tid < RS) { hr = 0; hc = tid; }
+    else if (tid < 2 * RS) { hr = TY + 1; hc = tid - RS; }
+    else if (tid < 2 * RS + TY) { hr = tid - 2 * RS + 1; hc = 0; }
+    else if (ring) { hr = tid - 2 * RS - TY + 1; hc = TZ + 1; }
+    const int hs = hr * RS + hc;
+    const uint32_t hcol = (uint32_t)wrap_coord(y0 - 1 + hr, a.Y) * sy + (uint32_t)wrap_coord(z0 - 1 + hc, a.Z);
+    const int o = (ty + 1) * RS + tz + 1;
+    const uint32_t last = (uint32_t)(a.X - 1) * sx;
+    auto adv = [&](uint32_t p) { return (p == last) ? 0u : p + sx; };
+    auto plane = [&](int x) { return (uint32_t)wrap_coord(x, a.X) * sx; };
+    double s = 0.0;
+    griddep_launch();
+    griddep_wait();
+
+    // planes x0-1 and x0 go straight into the window; plane x0+1 waits in registers
+    uint32_t pc = plane(x0), pn = plane(x0 + 1);
+    {
+        const uint32_t pm = plane(x0 - 1);
+        tile[(x0 + 3) & 3][o] = u[pm + col];        // slot of plane x is x & 3; x0-1 = x0+3 (mod 4)
+        tile[x0 & 3][o] = u[pc + col];
+        if (ring) {
+            tile[(x0 + 3) & 3][hs] = u[pm + hcol];
+            tile[x0 & 3][hs] = u[pc + hcol];
+        }
+    }
+    T un = u[pn + col], hn = T(0);
+    if (ring) hn = u[pn + hcol];
+    T d[6], dnext[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) d[q] = a.coef[q][pc + col];
+    for (int x = x0; x < x1; ++x) {
+        T *tp = tile[(x + 1) & 3];
+        tp[o] = un;
+        if (ring) tp[hs] = hn;
+        const uint32_t pn2 = adv(pn);
+        un = u[pn2 + col];
+        if (ring) hn = u[pn2 + hcol];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) dnext[q] = a.coef[q][pn + col];
+        __syncthreads();
+        const T *tm = tile[(x + 3) & 3], *tc = tile[x & 3];
+        const T uc = tc[o];
+        const T fx = R::mul(a.cx, R::sub(R::mul(d[0], R::sub(tm[o], uc)), R::mul(d[0], R::sub(uc, tp[o]))));
+        const T fy = R::mul(a.cy, R::sub(R::mul(d[1], R::sub(tc[o - RS], uc)), R::mul(d[1], R::sub(uc, tc[o + RS]))));
+        const T fz = R::mul(a.cz, R::sub(R::mul(d[2], R::sub(tc[o - 1], uc)), R::mul(d[2], R::sub(uc, tc[o + 1]))));
+        const T sp = R::add(R::add(fx, fy), fz);
+        // mixed terms (u[+a,+b] - u[+a,-b]) - (u[-a,+b] - u[-a,-b]); ex, ey, ez carry 2/(4 h_a h_b)
+        const T mxy = R::sub(R::sub(tp[o + RS], tp[o - RS]), R::sub(tm[o + RS], tm[o - RS]));
+        const T mxz = R::sub(R::sub(tp[o + 1], tp[o - 1]), R::sub(tm[o + 1], tm[o - 1]));
+        const T myz = R::sub(R::sub(tc[o + RS + 1], tc[o + RS - 1]), R::sub(tc[o - RS + 1], tc[o - RS - 1]));
+        const T cross = R::add(R::add(R::mul(R::mul(a.ex, d[3]), mxy), R::mul(R::mul(a.ey, d[4]), mxz)),
+                               R::mul(R::mul(a.ez, d[5]), myz));
+        const T unew = R::add(uc, R::mul(R::add(R::add(sp, cross), R::mul(a.rho, R::mul(uc, R::sub(T(1), uc)))), a.dt));
+        if (valid) {
+            out[pc + col] = unew;
+            if (counts(a, x)) s += (double)unew;
+        }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) d[q] = dnext[q];
+        pc = pn; pn = pn2;
+    }
+    step_end<T, 1>(a, sc, s, 0.0);
+}
+
+}  // namespace tgtk
