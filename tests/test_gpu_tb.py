@@ -90,3 +90,48 @@ def test_slab_blocks_with_two_step_launches(oracle, driver):
     for halo in (4, 5):
         got = slab.dti_loop(u0, rgb, 0.9, 0.2, 0.004, 1.0, 1.3, 0.7, 22, halo=halo, driver=driver)
         assert np.array_equal(got["state"], ref["state"]), halo
+
+
+# ---- FK -------------------------------------------------------------------------------------------------
+def _run_fk(shape, seed, nsteps, precision, tb, record=None, stopping_volume=np.inf, l2pf="-1"):
+    from tumorgrowthtoolkit_b200 import _loop
+    os.environ["TGTK_TB"], os.environ["TGTK_L2PF"] = str(tb), str(l2pf)
+    rng = np.random.default_rng(seed)
+    wm = rng.uniform(0, 1, shape) * (rng.uniform(0, 1, shape) < 0.8)
+    gm = rng.uniform(0, 1, shape) * (1 - wm)
+    u0 = rng.uniform(0, 1, shape) * (rng.uniform(0, 1, shape) < 0.6)
+    args = (u0, wm, gm, 0.1, 1.1, 10.0, 0.2, 0.02, 1.0, 1.3, 0.7)
+    return _loop.fk_loop(*args, nsteps, stopping_volume=stopping_volume, record_steps=record, precision=precision), args
+
+
+@settings(max_examples=30, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(shape=shapes, seed=st.integers(0, 2 ** 20), nsteps=st.integers(1, 75), precision=st.sampled_from(["fp64", "fp32"]),
+       l2pf=st.sampled_from(["0", "2"]))
+def test_fk_two_step_launches(oracle, shape, seed, nsteps, precision, l2pf):
+    """Same operator, different association of the face sums than fk_step_v4: equal to rounding, not bitwise."""
+    tol = 1e-12 if precision == "fp64" else 2e-5
+    a, args = _run_fk(shape, seed, nsteps, precision, 0, [nsteps - 1], l2pf=l2pf)
+    b, _ = _run_fk(shape, seed, nsteps, precision, 1, [nsteps - 1], l2pf=l2pf)
+    assert a["steps_run"] == b["steps_run"] == nsteps
+    assert np.max(np.abs(a["state"] - b["state"])) <= tol
+    assert abs(a["volume"] - b["volume"]) <= 10 * tol * max(1.0, abs(a["volume"]))
+    if nsteps >= 5:
+        assert b["launches"] < a["launches"]
+    ref = oracle.fk_loop(*args, nsteps)
+    assert np.max(np.abs(b["state"] - ref["state"])) <= tol
+
+
+def test_fk_stop_criterion_and_slab_with_two_step_launches(oracle):
+    from tumorgrowthtoolkit_b200 import slab
+    shape = (14, 19, 37)
+    free, args = _run_fk(shape, 5, 50, "fp64", 1)
+    th = free["volume"] * 0.97 if free["volume"] > _run_fk(shape, 5, 1, "fp64", 1)[0]["volume"] else free["volume"] * 1.03
+    a, _ = _run_fk(shape, 5, 50, "fp64", 0, np.arange(0, 50, 6), stopping_volume=th)
+    b, _ = _run_fk(shape, 5, 50, "fp64", 1, np.arange(0, 50, 6), stopping_volume=th)
+    assert a["stop"] == b["stop"] and a["steps_run"] == b["steps_run"] and a["t_stop"] == b["t_stop"]
+    assert np.max(np.abs(a["state"] - b["state"])) <= 1e-12
+    os.environ["TGTK_TB"] = "1"
+    ref = oracle.fk_loop(*args, 22)
+    for driver in ("p2p", "native", "torch"):
+        got = slab.fk_loop(*args, 22, halo=4, driver=driver)
+        assert np.max(np.abs(got["state"] - ref["state"])) <= 1e-12, driver

@@ -107,7 +107,7 @@ struct tgtk_sim {
     bool pads_dirty = true;
     int minb = 0;          // FK_2c staged kernel: resident blocks per SM the register budget targets
     unsigned partials_cap = 0;
-    // temporal blocking (tgtk_kernels_tb.cuh): two steps per launch where a kernel exists (FK_DTI) and the
+    // temporal blocking (tgtk_kernels_tb.cuh): two steps per launch where a kernel exists (FK, FK_DTI) and the
     // run is host-scheduled or speculative.  TGTK_TB: 1 on, 0 off, -1 auto (fp64 boxes of more than twice the L2)
     int tb = -1;
     int tb_rows = 18;      // thread rows of the two-step kernel's block: 18 (16 output rows, 576 threads) or 10 (8, 320)
@@ -657,12 +657,14 @@ static int configure_launch(tgtk_sim *s)
     drop_graph(s);
     // two-step kernel geometry: 30 x (rows - 2) output voxels per 32 x rows thread block, x cut into segments like above
     s->tb_nblocks = 0;
-    if (p.model == TGTK_MODEL_DTI && fits32) {
-        const int rows = (s->tb_rows == 10) ? 10 : 18, oy = rows - 2;
+    if ((p.model == TGTK_MODEL_DTI || p.model == TGTK_MODEL_FK) && fits32) {
+        const int rows = (s->tb_rows == 10 && p.model == TGTK_MODEL_DTI) ? 10 : 18, oy = rows - 2;
         const int tiles = ((p.Z + 29) / 30) * ((p.Y + oy - 1) / oy);
         int per_sm = 2, sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
-        const void *fn = (p.dtype == TGTK_F64)
+        const void *fn = (p.model == TGTK_MODEL_FK)
+                             ? ((p.dtype == TGTK_F64) ? (const void *)fk_step2_tb<double, 18, 2> : (const void *)fk_step2_tb<float, 18, 2>)
+                         : (p.dtype == TGTK_F64)
                              ? (rows == 10 ? (const void *)dti_step2_tb<double, 10, 3> : (const void *)dti_step2_tb<double, 18, 2>)
                              : (rows == 10 ? (const void *)dti_step2_tb<float, 10, 3> : (const void *)dti_step2_tb<float, 18, 2>);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 32 * rows, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
@@ -727,7 +729,8 @@ static bool tb_enabled(const tgtk_sim *s)
     // roofline -- fp64 boxes well beyond L2 (+20 % at 28 M voxels) -- and is level or behind elsewhere
     const tgtk_params &p = s->p;
     const double touched = (double)(2 * s->nfields + s->ncoef) * (double)p.X * (double)s->sx * (double)s->elem;
-    return p.dtype == TGTK_F64 && touched > 2.0 * (double)s->l2_bytes;
+    // (FK: the two-step kernel is correct but 14 % behind the two-voxel one-step kernel even at 28 M voxels -- opt-in only)
+    return p.model == TGTK_MODEL_DTI && p.dtype == TGTK_F64 && touched > 2.0 * (double)s->l2_bytes;
 }
 
 // two steps in one launch: reads state[par], writes state[par ^ 1], partial sums into ring slots slot, slot + 1
@@ -739,14 +742,17 @@ static cudaError_t launch_pair(tgtk_sim *s, int par, int slot)
     s->grid = s->tb_grid;
     s->block = s->tb_block;
     cudaError_t e;
+    const bool fk = (s->p.model == TGTK_MODEL_FK);
     if (s->p.dtype == TGTK_F64) {
         StepArgs<double> a;
         fill_args(s, a);
-        e = (s->tb_rows == 10) ? launch_v4(s, dti_step2_tb<double, 10, 3>, a, s->tb_lx) : launch_v4(s, dti_step2_tb<double, 18, 2>, a, s->tb_lx);
+        if (fk) e = launch_v4(s, fk_step2_tb<double, 18, 2>, a, s->tb_lx);
+        else e = (s->tb_rows == 10) ? launch_v4(s, dti_step2_tb<double, 10, 3>, a, s->tb_lx) : launch_v4(s, dti_step2_tb<double, 18, 2>, a, s->tb_lx);
     } else {
         StepArgs<float> a;
         fill_args(s, a);
-        e = (s->tb_rows == 10) ? launch_v4(s, dti_step2_tb<float, 10, 3>, a, s->tb_lx) : launch_v4(s, dti_step2_tb<float, 18, 2>, a, s->tb_lx);
+        if (fk) e = launch_v4(s, fk_step2_tb<float, 18, 2>, a, s->tb_lx);
+        else e = (s->tb_rows == 10) ? launch_v4(s, dti_step2_tb<float, 10, 3>, a, s->tb_lx) : launch_v4(s, dti_step2_tb<float, 18, 2>, a, s->tb_lx);
     }
     s->grid = g;
     s->block = b;

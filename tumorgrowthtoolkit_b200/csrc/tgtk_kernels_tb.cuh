@@ -152,6 +152,103 @@ __global__ void __launch_bounds__(32 * TYT, MINB) dti_step2_tb(const StepArgs<T>
     finish_light_pair(a, sum1, sum2);
 }
 
+// FK with two time steps per launch: the same two pipelines as dti_step2_tb.  The face coefficients are
+// relu(k(c) + k(c')) (tgtk_kernels_v3.cuh), so the U0 plane in shared memory carries (u, k) pairs on the
+// extended tile plus ring, and the U1 plane carries (u1, k) pairs too (k copied along: U2's neighbours then
+// come with one 128-bit read each, and the U0 buffer that the next iteration overwrites is never read late).
+// Own-column k of planes x-2 .. x+1 stays in registers.
+template <typename T, int TYT, int MINB>
+__global__ void __launch_bounds__(32 * TYT, MINB) fk_step2_tb(const StepArgs<T> a, const int lx)
+{
+    constexpr int TZT = 32, OZ = TZT - 2, OY = TYT - 2;
+    constexpr int RS0 = TZT + 2, PL0 = (TYT + 2) * RS0;
+    constexpr int RS1 = TZT, PL1 = TYT * RS1;
+    __shared__ Pair<T> s0[2][PL0];         // (u0, k) of plane xi on E1 + ring
+    __shared__ Pair<T> s1[2][PL1];         // (u1, k) of plane xi on E1
+    const StepCtl sc = step_begin(a);
+    if (sc.stop) return;
+    const T *__restrict__ u = a.buf[sc.par][0];
+    T *__restrict__ out = a.buf[sc.par ^ 1][0];
+    const T *__restrict__ kc = a.coef[0];
+    const int tz = threadIdx.x, ty = threadIdx.y, tid = ty * TZT + tz;
+    const int z0 = blockIdx.x * OZ, y0 = blockIdx.y * OY;
+    const int zc = z0 - 1 + tz, yc = y0 - 1 + ty;
+    const bool is_out = tz >= 1 && tz <= OZ && ty >= 1 && ty <= OY && zc < a.Z && yc < a.Y;
+    const int x0 = blockIdx.z * lx, x1 = min(x0 + lx, a.X);
+    const uint32_t sx = (uint32_t)a.sx, sy = (uint32_t)a.sy;
+    const uint32_t col = (uint32_t)wrap_coord(yc, a.Y) * sy + (uint32_t)wrap_coord(zc, a.Z);
+    const bool ring = tid < 2 * TZT + 2 * TYT;
+    int hr = 1, hc = 1;
+    if (tid < TZT) { hr = 0; hc = tid + 1; }
+    else if (tid < 2 * TZT) { hr = TYT + 1; hc = tid - TZT + 1; }
+    else if (tid < 2 * TZT + TYT) { hr = tid - 2 * TZT + 1; hc = 0; }
+    else if (ring) { hr = tid - 2 * TZT - TYT + 1; hc = TZT + 1; }
+    const int hs = hr * RS0 + hc;
+    const uint32_t hcol = (uint32_t)wrap_coord(y0 - 2 + hr, a.Y) * sy + (uint32_t)wrap_coord(z0 - 2 + hc, a.Z);
+    const int o0 = (ty + 1) * RS0 + tz + 1, o1 = ty * RS1 + tz;
+    auto plane = [&](int x) { return (uint32_t)wrap_coord(x, a.X) * sx; };
+    L2Strip pf;
+    {
+        const int r0 = max(y0 - 2, 0), r1 = min(y0 + TYT, a.Y);
+        pf.on = a.l2pf > 0 && blockIdx.x == 0 && tid == 0 && r1 > r0;
+        pf.row0 = (uint32_t)r0 * sy;
+        pf.count = (uint32_t)max(r1 - r0, 0) * sy;
+        pf.plane = sx;
+        pf.total = (uint32_t)a.X * sx;
+    }
+    // FK.py:36-41 with the face coefficients of FK.py:12-26 in the compact form of fk_step_v4
+    auto one = [&](T c, T k, T um, T km, T up, T kp, T uym, T kym, T uyp, T kyp, T uzm, T kzm, T uzp, T kzp) {
+        T sp = a.cx * (relu(km + k) * (um - c) - relu(k + kp) * (c - up));
+        sp += a.cy * (relu(kym + k) * (uym - c) - relu(k + kyp) * (c - uyp));
+        sp += a.cz * (relu(kzm + k) * (uzm - c) - relu(k + kzp) * (c - uzp));
+        return c + a.dt * (sp + a.rho * c * (T(1) - c));
+    };
+    double sum1 = 0.0, sum2 = 0.0;
+    griddep_launch();
+    griddep_wait();
+
+    int xi = x0 - 1;
+    T u0m = u[plane(xi - 1) + col], u0c = u[plane(xi) + col], u0p = u[plane(xi + 1) + col];
+    T kmm = kc[plane(xi - 2) + col], km = kc[plane(xi - 1) + col], kk = kc[plane(xi) + col], kp = kc[plane(xi + 1) + col];
+    const uint32_t last = (uint32_t)(a.X - 1) * sx;
+    auto adv = [&](uint32_t o) { return (o == last) ? 0u : o + sx; };
+    uint32_t pw = plane(xi - 1), pn = plane(xi + 1), pn2 = plane(xi + 2);
+    T u1mm = T(0), u1m = T(0);
+    T hu = T(0), hk = T(0);
+    if (ring) { hu = u[plane(xi) + hcol]; hk = kc[plane(xi) + hcol]; }
+    int buf = 0;
+    for (; xi <= x1; ++xi) {
+        Pair<T> *t0 = s0[buf], *t1 = s1[buf];
+        t0[o0] = Pair<T>{u0c, kk};
+        if (ring) t0[hs] = Pair<T>{hu, hk};
+        const T u0n = u[pn2 + col], kn = kc[pn2 + col];
+        if (ring) { hu = u[pn + hcol]; hk = kc[pn + hcol]; }
+        if (pf.on) {
+            const uint32_t q = plane(xi + 2 + a.l2pf) + pf.row0;
+            l2_prefetch_strip(u, q, pf.count, pf.total); l2_prefetch_strip(kc, q, pf.count, pf.total);
+        }
+        __syncthreads();
+        const Pair<T> ym = t0[o0 - RS0], yp = t0[o0 + RS0], zm = t0[o0 - 1], zp = t0[o0 + 1];
+        const T u1c = one(u0c, kk, u0m, km, u0p, kp, ym.a, ym.b, yp.a, yp.b, zm.a, zm.b, zp.a, zp.b);
+        t1[o1] = Pair<T>{u1c, kk};
+        if (is_out && xi >= x0 && xi < x1 && counts(a, xi)) sum1 += (double)u1c;
+        __syncthreads();
+        if (is_out && xi > x0) {             // U2[xi-1]: u1 of planes xi-2, xi-1, xi; k of the same planes
+            const Pair<T> *tp = s1[buf ^ 1];
+            const Pair<T> vm = tp[o1 - RS1], vp = tp[o1 + RS1], wm = tp[o1 - 1], wp = tp[o1 + 1];
+            const T u2 = one(u1m, km, u1mm, kmm, u1c, kk, vm.a, vm.b, vp.a, vp.b, wm.a, wm.b, wp.a, wp.b);
+            out[pw + col] = u2;
+            if (counts(a, xi - 1)) sum2 += (double)u2;
+        }
+        u0m = u0c; u0c = u0p; u0p = u0n;
+        kmm = km; km = kk; kk = kp; kp = kn;
+        u1mm = u1m; u1m = u1c;
+        pw = adv(pw); pn = adv(pn); pn2 = adv(pn2);
+        buf ^= 1;
+    }
+    finish_light_pair(a, sum1, sum2);
+}
+
 }  // namespace tgtk
 
 // =====================================================================================================
