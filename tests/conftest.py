@@ -12,6 +12,13 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # property tests draw the same examples on every box: a round-end run checks what the development runs checked
+    try:
+        from hypothesis import settings
+        settings.register_profile("tgtk", derandomize=True, deadline=None, database=None)
+        settings.load_profile("tgtk")
+    except ImportError:
+        pass
 
 
 @pytest.fixture(scope="session")
