@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libtgtk_b200.so")
+LIB_PATH = os.environ.get("TGTK_LIB_PATH") or os.path.join(_HERE, "csrc", "libtgtk_b200.so")   # override: A/B builds
 
 MODEL_FK, MODEL_FK_2C, MODEL_DTI, MODEL_COEF6, MODEL_FK_FACES, MODEL_FK2C_COEF12, MODEL_DTI_FULL = 0, 1, 2, 3, 4, 5, 6
 F64, F32 = 0, 1

@@ -156,6 +156,9 @@ __device__ __forceinline__ float tg_max(float a, float b) { return fmaxf(a, b); 
 // fix-up) and sits on the fp64 pipe; masking with the sign bit is 3 integer ops.
 __device__ __forceinline__ double relu(double x)
 {
+#ifdef TGTK_RELU_ABS
+    return 0.5 * (x + fabs(x));     // experiment: |x| is an operand modifier, two fp64-pipe instructions instead of three ALU ones
+#endif
     const int hi = __double2hiint(x);
     const int keep = ~(hi >> 31);
     return __hiloint2double(hi & keep, __double2loint(x) & keep);
