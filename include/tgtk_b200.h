@@ -165,7 +165,16 @@ int tgtk_sim_run_slab(tgtk_sim *sim, void *comm, int nsteps, int halo, int owned
 int tgtk_sim_ipc_export(tgtk_sim *sim, unsigned char *out);
 int tgtk_sim_ipc_connect(tgtk_sim *sim, const unsigned char *prev, const unsigned char *next, int same_peer);
 int tgtk_sim_run_slab_p2p(tgtk_sim *sim, int nsteps, int halo, int owned, int prev_owned);
-/* 0, or which handshake of the peer-to-peer driver timed out (1: block done, 2: ghosts pushed). */
+/* Fused slab driver (the default of slab.py): X = owned + 2, one ghost plane per side.  After this call tgtk_sim_run
+ * steps planes [1, 1 + owned) only; the blocks of the STEP KERNEL that compute a boundary plane also store it into the
+ * neighbouring rank's ghost plane (peer-mapped memory over NVLink) and publish the launch's epoch in the neighbour's
+ * flag word, the blocks that read a ghost plane wait for the neighbour's previous epoch -- no exchange launches, no
+ * copies between steps, interior blocks never wait.  Per chunk of steps the volumes are summed over the ranks
+ * (ncclAllReduce on `comm`; NULL: one rank) before the reference's stop tests (FK/FK.py:216-218,
+ * FK_DTI/FK_DTI.py:199-206) run on them, so stopping_volume, the `volume < 1e-6` exit, snapshots and tgtk_sim_reset
+ * work as on one GPU.  All ranks must issue the same run / sync / reset sequence. */
+int tgtk_sim_slab_attach(tgtk_sim *sim, void *comm, int owned, int prev_owned);
+/* 0, or which handshake timed out (p2p driver: 1 block done, 2 ghosts pushed; fused driver: 3). */
 int tgtk_sim_slab_error(tgtk_sim *sim, int *err);
 
 /* Host -> device.  `host` is float64 with element strides (sx,sy,sz); any strides are

@@ -71,7 +71,8 @@ def test_cuda_kernel_large_batch_properties():
 
 @pytest.mark.gpu
 def test_solver_backend_switch():
-    """FK_DTI_Solver with elongation_backend='cuda' stays within the fp64 gate of the default torch path."""
+    """FK_DTI_Solver's default CUDA elongation stays within the fp64 gate of the literal torch restatement
+    (elongation_backend='torch', the reference's own float32 CPU eigh)."""
     from tumorgrowthtoolkit_b200.FK_DTI import FK_DTI_Solver
     from tumorgrowthtoolkit_b200 import synthetic
     wm, gm = synthetic.brain_phantom((40, 44, 36))
@@ -82,7 +83,7 @@ def test_solver_backend_switch():
     tensors = 0.5 * (tensors + np.swapaxes(tensors, -1, -2))
     base = dict(Dw=0.8, rho=0.3, diffusionEllipsoidScaling=1.8, diffusionTensors=tensors, NxT1_pct=0.5, NyT1_pct=0.5,
                 NzT1_pct=0.5, resolution_factor=1.0, stopping_time=12, init_scale=1.0)
-    a = FK_DTI_Solver(dict(base)).solve()
-    b = FK_DTI_Solver(dict(base, elongation_backend='cuda')).solve()
+    a = FK_DTI_Solver(dict(base, elongation_backend='torch')).solve()
+    b = FK_DTI_Solver(dict(base)).solve()
     assert a['success'] and b['success']
     assert np.max(np.abs(a['final_state'] - b['final_state'])) <= 1e-6

@@ -319,6 +319,6 @@ def test_slab_single_rank_equals_plain_loop(L):
     P0, N0, S0 = u0, 0.3 * u0[::-1], np.ones(shape)
     a2 = (P0, N0, S0, wm, gm, 0.1, 0.9, 1.0, 10.0, 1.3, 0.3, 0.35, 0.5, 0.05, 0.02, 1.0, 1.1, 0.9, 9)
     ref = _loop.fk2c_loop(*a2)
-    got = slab.fk2c_loop(*a2, halo=2)
+    got = slab.fk2c_loop(*a2, halo=2, driver="p2p")
     for k in "PNS":
         assert np.array_equal(got["state"][k], ref["state"][k]), k

@@ -62,6 +62,27 @@ def test_bitwise_equal_to_the_oracle(oracle):
     assert np.array_equal(b["state"], ref["state"])
 
 
+@pytest.mark.parametrize("nsteps", [5, 7, 38])
+def test_fp32_zpair_kernel_on_odd_z_with_two_step_launches_requested(oracle, nsteps):
+    """TGTK_TB=1 + the fp32 z-pair kernel (auto for FK_DTI) + odd Z + nsteps % 4 != 0 mixed
+    two-step launches, which do not write the z = Z mirror element, with z-pair leftovers that read it as their
+    periodic neighbour.  The combination now falls back to one-step launches: same bits as TGTK_TB=0, oracle-close."""
+    from tumorgrowthtoolkit_b200 import _loop
+    shape = (11, 14, 37)
+    rng = np.random.default_rng(3)
+    rgb = rng.uniform(0.5, 3, shape + (3,))
+    u0 = rng.uniform(0, 1, shape)
+    args = (u0, rgb, 0.9, 0.2, 0.004, 1.0, 1.3, 0.7, nsteps)
+    os.environ.pop("TGTK_VARIANT", None)
+    os.environ["TGTK_TB"] = "0"
+    a = _loop.dti_loop(*args, precision="fp32")
+    os.environ["TGTK_TB"] = "1"
+    b = _loop.dti_loop(*args, precision="fp32")
+    assert np.array_equal(a["state"], b["state"])
+    ref = oracle.dti_loop(*args)
+    assert np.max(np.abs(b["state"] - ref["state"])) <= 2e-5
+
+
 @pytest.mark.parametrize("spec", ["0", "1"])
 def test_stop_criterion_with_two_step_launches(spec):
     os.environ["TGTK_SPECULATE"] = spec

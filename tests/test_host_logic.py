@@ -16,7 +16,7 @@ from tests.solve_cases import FK_CASES, C2_CASES, DTI_CASES, base_params, dti_pa
 @pytest.fixture()
 def cpu_loops(monkeypatch, oracle):
     def drop(kw):
-        for k in ("precision", "device", "bit_exact"):
+        for k in ("precision", "device", "bit_exact", "devices"):
             kw.pop(k, None)
         return kw
     monkeypatch.setattr(_loop, "fk_loop", lambda *a, **kw: oracle.fk_loop(*a, **drop(kw)))
@@ -50,7 +50,9 @@ def test_fk2c_solve_host_logic(name, gold_solve, cpu_loops):
 @pytest.mark.parametrize("name", sorted(DTI_CASES))
 def test_dti_solve_host_logic(name, gold_solve, cpu_loops):
     tol = 2e-4 if name == "dti_elong" else 1e-12   # float32 eigh inside the reference's elongation
-    res = DTI(dti_params(gold_solve, DTI_CASES[name])).solve()
+    p = dti_params(gold_solve, DTI_CASES[name])
+    p["elongation_backend"] = "torch"              # no GPU here: the literal restatement of the reference's CPU eigh
+    res = DTI(p).solve()
     compare_result(name, res, gold_solve, tol=tol)
 
 

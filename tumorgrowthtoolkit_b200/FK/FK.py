@@ -7,6 +7,8 @@ reference's behaviour):
 
     precision   'fp64' (default) | 'fp32'   storage + arithmetic type of the loop
     device      CUDA device ordinal (default 0)
+    devices     'slab': decompose the grid along axis 0 over the ranks of the caller's torch.distributed group
+                (one process per GPU; every rank calls solve() and receives the same result dict)
     bit_exact   True: fp64 results equal numpy's bit for bit (slower face-array kernel)
 """
 import numpy as np
@@ -59,7 +61,13 @@ class Solver(BaseSolver):
         return A
 
     def _device(self):
-        return int(self.params.get('device', 0)) if isinstance(self.params, dict) else 0
+        p = self.params if isinstance(self.params, dict) else {}
+        if 'device' in p:
+            return int(p['device'])
+        if p.get('devices') == 'slab':          # one process per GPU (torchrun): each rank steps its slab on its own device
+            import os
+            return int(os.environ.get('LOCAL_RANK', 0))
+        return 0
 
     # ---- solve ------------------------------------------------------------------------------
     def solve(self):
@@ -107,7 +115,7 @@ class Solver(BaseSolver):
                                 th_matter, Dw, ratio, rho, dt, dx, dy, dz, nsteps,
                                 stopping_volume=stopping_volume, record_steps=record,
                                 precision=p.get('precision', 'fp64'), device=self._device(),
-                                bit_exact=bool(p.get('bit_exact', False)))
+                                bit_exact=bool(p.get('bit_exact', False)), devices=p.get('devices'))
             volume = np.float64(run['volume'])
             final_time = run['t_stop'] * dt if run['stop'] == 'volume' else stopping_time
 

@@ -88,7 +88,7 @@ class Solver(FK_Solver):
                               _host.crop(initial['S'], box), _host.crop(wm_lo, box), _host.crop(gm_lo, box),
                               th_matter, th_necro, Dw, ratio, D_s, rho, lambda_np, sigma_np, lambda_s,
                               dt, dx, dy, dz, nsteps, stopping_volume=stopping_volume, record_steps=record,
-                              precision=p.get('precision', 'fp64'), device=self._device())
+                              precision=p.get('precision', 'fp64'), device=self._device(), devices=p.get('devices'))
         volume = np.float64(run['volume'])
         final_time = run['t_stop'] * dt if run['stop'] == 'volume' else stopping_time
 

@@ -54,9 +54,10 @@ class FK_DTI_Solver(FK_Solver):
 
         tensors = p["diffusionTensors"]
         if scaling != 1:                                                # FK_DTI.py:107-110
-            # 'torch' (default): the reference's own float32 CPU eigh, bit-identical preprocessing;
-            # 'cuda': csrc/tgtk_elongate.cuh, equal to float32 rounding and ~100x faster on a full volume
-            backend = p.get('elongation_backend', 'torch')
+            # 'cuda' (default): csrc/tgtk_elongate.cuh, equal to the reference's float32 LAPACK path at float32
+            # rounding (1e-6 of the largest entry) and ~180x faster on a full volume; 'torch': opt-out, the
+            # reference's own float32 CPU eigh restated literally (bit-identical preprocessing, needs torch)
+            backend = p.get('elongation_backend', 'cuda')
             if backend == 'cuda':
                 tensors = tools.elongate_tensor_along_main_axis_cuda(tensors, scaling, device=self._device())
             elif backend == 'torch':
@@ -73,8 +74,9 @@ class FK_DTI_Solver(FK_Solver):
         _host.check_seed(pct)
 
         rgb_lo = _host.resample_linear(rgb, [res_factor, res_factor, res_factor, 1], device=self._device())
-        if doPlot:                                                      # plotting is out of scope
-            raise NotImplementedError("doPlot=True needs matplotlib and is not part of the time-stepping path")
+        if doPlot:          # FK_DTI.py:128-150 shows three matplotlib figures and carries on; plotting is out of
+            import warnings  # scope here, so the request is ignored rather than failing the solve
+            warnings.warn("doPlot=True is ignored: plotting is not part of the time-stepping path", stacklevel=2)
         grid = _host.LowResGrid(rgb_lo.shape, rgb.shape, res_factor, *spacing, pct)
         dx, dy, dz = grid.h
 
@@ -106,7 +108,7 @@ class FK_DTI_Solver(FK_Solver):
             else:
                 run = _loop.dti_loop(_host.crop(initial, box), _host.crop(rgb_lo, box), Dw, rho, dt, dx, dy, dz, nsteps,
                                      stopping_volume=stopping_volume, record_steps=record,
-                                     precision=p.get('precision', 'fp64'), device=self._device())
+                                     precision=p.get('precision', 'fp64'), device=self._device(), devices=p.get('devices'))
             if run['stop'] == 'small':
                 print("Volume is to small")                             # FK_DTI.py:203-206 (sic)
             volume = np.float64(run['volume'])

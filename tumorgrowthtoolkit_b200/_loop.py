@@ -47,12 +47,32 @@ def _finish(sim, nsteps, record_steps, fields, names):
     return res
 
 
+def _slab_requested(devices):
+    """params['devices'] == 'slab' (or TGTK_DEVICES=slab): decompose this solve over the ranks of the caller's
+    torch.distributed group (one process per GPU, every rank calls solve() with the same parameters and gets
+    the same result dict).  Anything else, or no initialised group of more than one rank: one GPU."""
+    import os
+    if (devices or os.environ.get("TGTK_DEVICES", "")) != "slab":
+        return False
+    try:
+        import torch.distributed as dist
+    except ImportError:
+        return False
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
 def fk_loop(u0, WM, GM, th, Dw, ratio, rho, dt, dx, dy, dz, nsteps, stopping_volume=np.inf,
-            record_steps=None, precision="fp64", device=0, bit_exact=False):
+            record_steps=None, precision="fp64", device=0, bit_exact=False, devices=None):
     """FK: get_D (FK.py:200) fused into the step kernel + the loop of FK.py:212-226.
     bit_exact=True builds the three face arrays in the reference's rounding order and steps
     them with unfused arithmetic (fp64 results then equal numpy's bit for bit)."""
     logical_or = bool(np.asarray(WM).dtype == np.bool_ and np.asarray(GM).dtype == np.bool_)
+    if _slab_requested(devices):
+        if bit_exact or logical_or:
+            raise ValueError("devices='slab' steps the compact FK kernel: bit_exact / boolean tissue maps are single-GPU modes")
+        from . import slab
+        return slab.fk_loop(u0, WM, GM, th, Dw, ratio, rho, dt, dx, dy, dz, nsteps, precision=precision, device=device,
+                            stopping_volume=stopping_volume, record_steps=record_steps)
     model = nat.MODEL_FK_FACES if (bit_exact or logical_or) else nat.MODEL_FK
     p = nat.make_params(model, dtype_code(precision), np.shape(u0), (dx, dy, dz), dt, rho=rho, Dw=Dw,
                         ratio=ratio, th_matter=th, stopping_volume=stopping_volume,
@@ -66,9 +86,13 @@ def fk_loop(u0, WM, GM, th, Dw, ratio, rho, dt, dx, dy, dz, nsteps, stopping_vol
 
 
 def dti_loop(u0, rgb, Dw, rho, dt, dx, dy, dz, nsteps, stopping_volume=np.inf, record_steps=None,
-             precision="fp64", device=0):
+             precision="fp64", device=0, devices=None):
     """FK_DTI: get_D_from_DTI (FK_DTI.py:174: D_a = rgb[...,a]*Dw, D_plus aliasing D_minus)
     + the loop of FK_DTI.py:195-214 incl. the `volume < 1e-6` exit."""
+    if _slab_requested(devices):
+        from . import slab
+        return slab.dti_loop(u0, rgb, Dw, rho, dt, dx, dy, dz, nsteps, precision=precision, device=device,
+                             stopping_volume=stopping_volume, small_volume=0.000001, record_steps=record_steps)
     p = nat.make_params(nat.MODEL_DTI, dtype_code(precision), np.shape(u0), (dx, dy, dz), dt, rho=rho, Dw=Dw,
                         stopping_volume=stopping_volume, small_volume=0.000001)
     rgb = np.asarray(rgb)
@@ -98,9 +122,14 @@ def dti_full_loop(u0, rgb, offdiag, Dw, rho, dt, dx, dy, dz, nsteps, stopping_vo
 
 
 def fk2c_loop(P0, N0, S0, WM, GM, th, th_necro, Dw, ratio, Ds, rho, lambda_np, sigma_np, lambda_s,
-              dt, dx, dy, dz, nsteps, stopping_volume=np.inf, record_steps=None, precision="fp64", device=0):
+              dt, dx, dy, dz, nsteps, stopping_volume=np.inf, record_steps=None, precision="fp64", device=0, devices=None):
     """FK_2c: get_D_with_necro + get_D(...,D_s,1) + FK_2c_update fused per step
     (FK_2c.py:215-216,229-230) + the loop of FK_2c.py:227-245."""
+    if _slab_requested(devices):
+        from . import slab
+        return slab.fk2c_loop(P0, N0, S0, WM, GM, th, th_necro, Dw, ratio, Ds, rho, lambda_np, sigma_np, lambda_s, dt, dx, dy, dz,
+                              nsteps, precision=precision, device=device, stopping_volume=stopping_volume,
+                              record_steps=record_steps)
     p = nat.make_params(nat.MODEL_FK_2C, dtype_code(precision), np.shape(P0), (dx, dy, dz), dt, rho=rho, Dw=Dw,
                         ratio=ratio, th_matter=th, th_necro=th_necro, Ds=Ds, lambda_np=lambda_np,
                         sigma_np=sigma_np, lambda_s=lambda_s, stopping_volume=stopping_volume)

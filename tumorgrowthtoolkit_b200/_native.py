@@ -75,6 +75,7 @@ def lib():
     L.tgtk_sim_ipc_connect.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
     L.tgtk_sim_run_slab_p2p.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.tgtk_sim_slab_error.argtypes = [vp, ctypes.POINTER(ctypes.c_int)]
+    L.tgtk_sim_slab_attach.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int]
     L.tgtk_sim_run_slab.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.tgtk_nccl_unique_id.argtypes = [ctypes.c_char_p]
     L.tgtk_nccl_comm_create.argtypes = [ctypes.POINTER(vp), ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
@@ -100,6 +101,16 @@ def lib():
     L.tgtk_sim_snapshot.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, _I64x3]
     L.tgtk_sim_device_ptr.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong), _I64x3,
                                       ctypes.POINTER(ctypes.c_int)]
+    # host-pointer entry points behind the reference's public per-step methods (_ops.py)
+    c_int, c_dbl = ctypes.c_int, ctypes.c_double
+    i64x6x3, ptr6 = (ctypes.c_int64 * 3) * 6, ctypes.c_void_p * 6
+    L.tgtk_fk_update_host.argtypes = [ctypes.POINTER(Params), c_int, vp, _I64x3, ptr6, i64x6x3]
+    L.tgtk_fk2c_update_host.argtypes = [ctypes.POINTER(Params), c_int, vp, _I64x3, vp, _I64x3, vp, _I64x3,
+                                        ptr6, i64x6x3, ptr6, i64x6x3]
+    L.tgtk_faces_host.argtypes = [c_int, c_int, c_int, c_int, vp, _I64x3, vp, _I64x3, vp, _I64x3, vp, _I64x3,
+                                  c_dbl, c_dbl, c_dbl, c_dbl, c_int, c_int, vp, vp, vp]
+    L.tgtk_resample_linear_host.argtypes = [c_int, vp, _I64x3, i3, i3, i3, vp, i3]
+    L.tgtk_elongate_tensors_host.argtypes = [c_int, vp, ctypes.c_int64, c_dbl, vp]
     if L.tgtk_abi_version() != 1:
         raise NativeError("libtgtk_b200.so ABI version mismatch")
     _lib = L
@@ -237,6 +248,9 @@ class Sim:
 
     def run_slab_p2p(self, nsteps, halo, owned, prev_owned):
         _check(lib().tgtk_sim_run_slab_p2p(self._h, int(nsteps), int(halo), int(owned), int(prev_owned)))
+
+    def slab_attach(self, comm, owned, prev_owned):
+        _check(lib().tgtk_sim_slab_attach(self._h, comm, int(owned), int(prev_owned)))
 
     def slab_error(self):
         e = ctypes.c_int(0)

@@ -141,6 +141,5 @@ def elongate_tensors(tensors, scale_factor, device=0):
     assert t.ndim >= 2 and t.shape[-2:] == (3, 3), "tensors must have shape (..., 3, 3)"
     out = np.empty(t.shape, dtype=np.float32)
     n = int(np.prod(t.shape[:-2], dtype=np.int64))
-    L.tgtk_elongate_tensors_host.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p]
     nat._check(L.tgtk_elongate_tensors_host(int(device), t.ctypes.data, n, float(scale_factor), out.ctypes.data))
     return out

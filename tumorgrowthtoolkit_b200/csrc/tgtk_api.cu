@@ -91,6 +91,12 @@ struct tgtk_sim {
     void *peer_state[2][2][3] = {};        // [prev|next][ping-pong][field]
     int *peer_flags[2] = {nullptr, nullptr};
     void *peer_opened[2][7] = {};          // pointers to close with cudaIpcCloseMemHandle
+    // fused slab mode (tgtk_sim_slab_attach): planes [1, 1 + slab_owned) are computed, the boundary planes are stored
+    // into the neighbours' ghost planes from inside the step kernels, volumes are all-reduced per chunk
+    bool slab_on = false;
+    int slab_owned = 0, slab_prev_owned = 0;
+    void *slab_comm = nullptr;             // NCCL communicator for the per-chunk all-reduce (nullptr: one rank)
+    double *chunkvol = nullptr;            // the chunk's local volumes, summed over the ranks in place
     bool host_sched = false;   // no stop criterion: parity baked into launches (see StepArgs)
     // A stop criterion is active: run host-scheduled all the same, chunk by chunk, behind a checkpoint of the
     // state; chunk_finish_kernel runs the stop tests afterwards and a trip is replayed from the checkpoint up to
@@ -330,6 +336,26 @@ template <typename T> static void fill_args(const tgtk_sim *s, StepArgs<T> &a)
     a.sum_x0 = s->sum_x0;
     a.sum_x1 = (s->sum_x1 < 0) ? p.X : s->sum_x1;
     a.l2pf = effective_l2pf(s);
+    a.x_lo = 0;
+    a.x_hi = p.X;
+    a.slab = 0;
+    if (s->slab_on) {
+        a.slab = 1;
+        a.x_lo = 1;
+        a.x_hi = 1 + s->slab_owned;
+        for (int b = 0; b < 2; ++b)
+            for (int f = 0; f < 3; ++f) {
+                a.peer_lo[b][f] = (T *)s->peer_state[0][b][f];
+                a.peer_hi[b][f] = (T *)s->peer_state[1][b][f];
+            }
+        // my plane 1 is the previous rank's upper ghost (its plane 1 + prev_owned); my plane `owned` is the next rank's plane 0
+        a.off_lo = (uint32_t)((int64_t)s->slab_prev_owned * s->sx);
+        a.off_hi = (uint32_t)(-(int64_t)s->slab_owned * s->sx);
+        a.flags = s->slab_flags;
+        a.flag_lo = s->peer_flags[0] + kSlabFromNext;     // I am the previous rank's "next"
+        a.flag_hi = s->peer_flags[1] + kSlabFromPrev;
+        a.ntiles = s->grid.x * s->grid.y;
+    }
 }
 
 // variant 0 = auto = the staged kernels with two voxels per thread (v4), fastest for every model and
@@ -347,6 +373,7 @@ static bool has_v5(const tgtk_sim *s)
 // pay for the scalar left / right reads with shared-memory bank conflicts.
 static int effective_variant(const tgtk_sim *s)
 {
+    if (s->slab_on) return 4;              // the in-kernel halo push lives in the two-voxel kernels
     if (s->variant == 0) return (has_v5(s) && s->p.model == TGTK_MODEL_DTI) ? 6 : 4;
     if (s->variant >= 5) return has_v5(s) ? s->variant : 4;
     return s->variant;
@@ -579,6 +606,7 @@ static int configure_launch(tgtk_sim *s)
     const tgtk_params &p = s->p;
     const bool fits32 = (uint64_t)p.X * (uint64_t)s->sx < (1ull << 31);   // 32-bit element offsets
     const int variant = effective_variant(s);
+    const int NX = s->slab_on ? s->slab_owned : p.X;       // planes a launch computes
     if (variant >= 2 && has_v2(p.model) && fits32) {
         int best_tz = 32;
         double best = 1e30;
@@ -617,16 +645,16 @@ static int configure_launch(tgtk_sim *s)
         const int nthreads = (four || zp1) ? 128 : two_rows ? tz * v4rows : 256;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, nthreads, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
         const double slots = (double)sms * per_sm;
-        int best_lx = p.X;
+        int best_lx = NX;
         double best_eff = -1.0;
-        for (int lx = 1; lx <= p.X; ++lx) {
-            const int ns = (p.X + lx - 1) / lx;
+        for (int lx = 1; lx <= NX; ++lx) {
+            const int ns = (NX + lx - 1) / lx;
             const double waves = tiles * (double)ns / slots;
-            const double eff = waves / std::ceil(waves) * (lx / (lx + 0.6)) * ((double)p.X / ((double)ns * lx));
+            const double eff = waves / std::ceil(waves) * (lx / (lx + 0.6)) * ((double)NX / ((double)ns * lx));
             if (eff > best_eff + 1e-9) { best_eff = eff; best_lx = lx; }
         }
         s->lx = best_lx;
-        const int nseg = (p.X + s->lx - 1) / s->lx;
+        const int nseg = (NX + s->lx - 1) / s->lx;
         s->block = dim3((four || zp1) ? 16 : tz, two_rows ? v4rows : ty, 1);
         s->grid = dim3((p.Z + tz - 1) / tz, (p.Y + ty - 1) / ty, nseg);
     } else if (p.model == TGTK_MODEL_DTI_FULL && variant >= 3 && fits32) {
@@ -723,7 +751,10 @@ static cudaError_t launch_one(tgtk_sim *s, int par, int slot)
 
 static bool tb_enabled(const tgtk_sim *s)
 {
-    if (s->tb_nblocks == 0 || !(s->host_sched || s->spec) || s->replaying) return false;
+    if (s->tb_nblocks == 0 || !(s->host_sched || s->spec) || s->replaying || s->slab_on) return false;
+    // the two-step kernels do not write the z = Z mirror element the fp32 z-pair kernels read as their periodic
+    // neighbour: a chunk that mixes both families on an odd-Z box would step its leftovers on a stale mirror
+    if (zpair_variant(s) && s->sy != s->p.Z) return false;
     if (s->tb >= 0) return s->tb != 0;
     // auto: measured on B200 the two-step kernel wins where the one-step kernel sits on the HBM
     // roofline -- fp64 boxes well beyond L2 (+20 % at 28 M voxels) -- and is level or behind elsewhere
@@ -784,15 +815,26 @@ static cudaError_t launch_steps(tgtk_sim *s, int par0, int n)
     return e;
 }
 
+static cudaError_t slab_allreduce(tgtk_sim *s, int count);   // tgtk_nccl.inc
+
 static cudaError_t launch_chunk_finish(tgtk_sim *s, int count)
 {
     const tgtk_params &p = s->p;
+    const int spec = (s->spec && !s->replaying) ? 1 : 0;
     ++s->aux_launches;
     chunk_finish_kernel<<<count, 256, 0, s->stream>>>(s->ctrl, s->partials, s->volumes, s->volumes_cap, s->nblocks, s->nfields,
-                                                   count, p.h[0] * p.h[1] * p.h[2], 1.0, (s->spec && !s->replaying) ? 1 : 0,
+                                                   count, p.h[0] * p.h[1] * p.h[2], 1.0, spec,
                                                    p.stopping_volume, p.small_volume, s->ring_stride, s->tb_nblocks,
-                                                   s->chunk_tb_mask);
+                                                   s->chunk_tb_mask, s->slab_on ? s->chunkvol : nullptr);
     s->chunk_tb_mask = 0;
+    cudaError_t e = cudaGetLastError();
+    if (!s->slab_on || e != cudaSuccess) return e;
+    // fused slab mode: sum the chunk's volumes over the ranks, then log them, run the stop tests, advance the counters
+    e = slab_allreduce(s, count);
+    if (e != cudaSuccess) return e;
+    ++s->aux_launches;
+    chunk_commit_kernel<<<1, 32, 0, s->stream>>>(s->ctrl, s->chunkvol, s->volumes, s->volumes_cap, count, spec, p.stopping_volume,
+                                               p.small_volume, s->slab_flags);
     return cudaGetLastError();
 }
 
@@ -803,7 +845,7 @@ static cudaError_t launch_checkpoint(tgtk_sim *s, int par)
     ++s->aux_launches;
     checkpoint_kernel<<<grid_1d(n8), 256, 0, s->stream>>>(s->ctrl, (const uint2 *)s->state[par][0], (const uint2 *)s->state[par][1],
                                                        (const uint2 *)s->state[par][2], (uint2 *)s->ckpt[0], (uint2 *)s->ckpt[1],
-                                                       (uint2 *)s->ckpt[2], n8);
+                                                       (uint2 *)s->ckpt[2], n8, s->slab_on ? s->slab_flags : nullptr);
     return cudaGetLastError();
 }
 
@@ -1101,6 +1143,7 @@ void tgtk_sim_destroy(tgtk_sim *s)
     sim_free(s, s->ctrl);
     sim_free(s, s->partials);
     sim_free(s, s->volumes);
+    sim_free(s, s->chunkvol);
     pinned_ctrl_put(s->ctrl_host);
     slab_p2p_close(s);
     drop_graph(s);
@@ -1299,7 +1342,7 @@ int tgtk_sim_prepare(tgtk_sim *s)
         const char *v = getenv("TGTK_HOST_SCHED");
         const bool host_sched = want && !(v && atoi(v) == 0);
         const char *w = getenv("TGTK_SPECULATE");
-        const bool spec = !want && !(w && atoi(w) == 0);
+        const bool spec = !want && (s->slab_on || !(w && atoi(w) == 0));   // a decomposed run has no device-scheduled mode
         if (host_sched != s->host_sched || spec != s->spec) drop_graph(s);
         s->host_sched = host_sched;
         s->spec = spec;
@@ -1359,8 +1402,13 @@ int tgtk_sim_run(tgtk_sim *s, int nsteps, const int32_t *record_steps, int nreco
     for (int i = r; i < nrecord; ++i)
         if (record_steps[i] < s->t_enqueued + nsteps && (i == r || record_steps[i] != record_steps[i - 1])) ++nsnap;
     std::vector<void *> arenas(nsnap, nullptr);
-    for (int i = 0; i < nsnap; ++i) CU(sim_malloc(s, (void **)(&arenas[i]), bytes * s->nfields));
     int used = 0;
+    // arenas not handed to s->snaps go back to the pool on EVERY exit, the error returns included
+    struct ArenaGuard {
+        tgtk_sim *s; std::vector<void *> &a; int &used;
+        ~ArenaGuard() { for (size_t i = (size_t)used; i < a.size(); ++i) sim_free(s, a[i]); }
+    } arena_guard{s, arenas, used};
+    for (int i = 0; i < nsnap; ++i) CU(sim_malloc(s, (void **)(&arenas[i]), bytes * s->nfields));
     s->replay_ms = 0.f;
     CU(cudaEventRecord(s->ev0, s->stream));
     int q = 0;
@@ -1401,7 +1449,6 @@ int tgtk_sim_run(tgtk_sim *s, int nsteps, const int32_t *record_steps, int nreco
             while (r < nrecord && record_steps[r] == t) ++r;
         }
     }
-    for (int i = used; i < nsnap; ++i) sim_free(s, arenas[i]);
     CU(cudaEventRecord(s->ev1, s->stream));
     s->timed = true;
     return 0;

@@ -57,7 +57,93 @@ template <typename T> struct StepArgs {
     // marching kernels: planes ahead of the current one whose lines are requested into L2
     // (prefetch.global.L2, fire and forget); 0 = off
     int l2pf;
+    // planes [x_lo, x_hi) of axis 0 are computed by this launch (two-voxel kernels; default: the whole box)
+    int x_lo, x_hi;
+    // Fused slab mode (tgtk_nccl.inc, one rank per GPU, axis 0 decomposed, one ghost plane per side): the blocks
+    // that compute the rank's lowest / highest owned plane ALSO store it into the neighbouring rank's ghost plane
+    // (peer-mapped memory, NVLink) and the last such block of the launch publishes the launch's epoch in the
+    // neighbour's flag word; the blocks that READ a ghost plane first wait until the neighbour has published the
+    // previous epoch.  No exchange launches, no copies between steps; interior blocks never wait.
+    int slab;                 // 0: off
+    T *peer_lo[2][3];         // previous rank's state buffers [ping-pong][field]
+    T *peer_hi[2][3];         // next rank's
+    uint32_t off_lo, off_hi;  // added (mod 2^32) to an element offset in my plane x_lo / x_hi-1: the neighbour's ghost element
+    int *flags;               // my words (SlabWord): written by the neighbours
+    int *flag_lo, *flag_hi;   // the word this rank publishes in the previous / next rank's memory
+    unsigned ntiles;          // blocks per plane segment (gridDim.x * gridDim.y)
 };
+
+// words of the slab flag array (one cudaMalloc per rank, mapped by both neighbours)
+enum SlabWord { kSlabFromPrev = 8, kSlabFromNext = 9, kSlabEpoch = 10, kSlabTicketLo = 12, kSlabTicketHi = 13, kSlabError = 4 };
+
+__device__ __forceinline__ int ld_acquire_sys(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int *p, int v)
+{
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// one thread: wait until the words `w0`, `w1` (-1: skip) of `flags` have reached `epoch`; gives up after 20 s
+__device__ __forceinline__ void slab_spin(int *flags, int w0, int w1, int epoch)
+{
+    unsigned long long t0 = 0, t1;
+    for (unsigned it = 0;; ++it) {
+        const bool ok0 = w0 < 0 || ld_acquire_sys(flags + w0) >= epoch;
+        const bool ok1 = w1 < 0 || ld_acquire_sys(flags + w1) >= epoch;
+        if (ok0 && ok1) break;
+        if ((it & 63u) == 0u) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t0 == 0) t0 = t1;
+            else if (t1 - t0 > 20000000000ull) { ((volatile int *)flags)[kSlabError] = 3; break; }   // report instead of hanging
+        }
+    }
+}
+
+struct SlabCtl {
+    bool lo, hi;   // this block computes the rank's lowest / highest owned plane (reads that ghost, pushes that plane)
+    int epoch;     // of this launch
+};
+
+// after griddep_wait(), before the first state access of the block
+template <typename T> __device__ __forceinline__ SlabCtl slab_begin(const StepArgs<T> &a, int x0, int x1)
+{
+    SlabCtl c;
+    c.lo = c.hi = false;
+    c.epoch = 0;
+    if (!a.slab) return c;
+    c.lo = (x0 == a.x_lo);
+    c.hi = (x1 == a.x_hi);
+    c.epoch = a.flags[kSlabEpoch] + a.slot + 1;      // only chunk_commit_kernel writes the base, never beside a step launch
+    if (c.lo || c.hi) {
+        if (threadIdx.x == 0 && threadIdx.y == 0) slab_spin(a.flags, c.lo ? kSlabFromPrev : -1, c.hi ? kSlabFromNext : -1, c.epoch - 1);
+        __syncthreads();
+    }
+    return c;
+}
+
+// after the last plane of the block: its pushes are made visible system-wide, the last block of each side publishes the epoch
+template <typename T> __device__ __forceinline__ void slab_end(const StepArgs<T> &a, const SlabCtl &c)
+{
+    if (!(c.lo || c.hi)) return;
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        __threadfence_system();
+        if (c.lo && atomicAdd((unsigned *)(a.flags + kSlabTicketLo), 1u) == a.ntiles - 1) {
+            a.flags[kSlabTicketLo] = 0;
+            __threadfence_system();
+            st_release_sys(a.flag_lo, c.epoch);
+        }
+        if (c.hi && atomicAdd((unsigned *)(a.flags + kSlabTicketHi), 1u) == a.ntiles - 1) {
+            a.flags[kSlabTicketHi] = 0;
+            __threadfence_system();
+            st_release_sys(a.flag_hi, c.epoch);
+        }
+    }
+}
 
 // L2 prefetch of the rows [y0, y0+rows) of plane xp of one array: rows of a plane are contiguous
 // (axis 2 fastest), so the whole strip -- every z tile of it -- is ONE bulk request to the TMA unit
@@ -305,8 +391,10 @@ __global__ void __launch_bounds__(256) chunk_finish_kernel(Ctrl *ctrl, const dou
                                                            int volumes_cap, unsigned nblocks, int nfields, int count,
                                                            double scale_p, double scale_n, int spec, double stop_volume,
                                                            double small_volume, unsigned ring_stride, unsigned nblocks_tb,
-                                                           unsigned tb_mask)
+                                                           unsigned tb_mask, double *chunkvol)
 {
+    // chunkvol != nullptr (fused slab mode): only deposit the chunk's LOCAL volumes there; chunk_commit_kernel logs
+    // them, runs the stop tests and advances the counters once they have been summed over the ranks
     __shared__ double red[2][8];
     if (spec && *(volatile const int *)&ctrl->stop_reason != 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -328,6 +416,7 @@ __global__ void __launch_bounds__(256) chunk_finish_kernel(Ctrl *ctrl, const dou
         for (int w = 0; w < 8; ++w) { a0 += red[0][w]; a1 += red[1][w]; }
         double vol = scale_p * a0;
         if (nfields > 1) vol += scale_n * a1;
+        if (chunkvol) { chunkvol[j] = vol; return; }
         if (t0 + j < volumes_cap) volumes[t0 + j] = vol;
         if (!spec && j == count - 1) ctrl->last_volume = vol;
         __threadfence();
@@ -359,11 +448,48 @@ __global__ void __launch_bounds__(256) chunk_finish_kernel(Ctrl *ctrl, const dou
     }
 }
 
+// fused slab mode: the second half of chunk_finish_kernel, after the chunk's volumes have been all-reduced
+__global__ void chunk_commit_kernel(Ctrl *ctrl, const double *chunkvol, double *volumes, int volumes_cap, int count, int spec,
+                                    double stop_volume, double small_volume, int *flags)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (spec && ctrl->stop_reason != 0) return;       // a voided chunk: its launches published nothing, the epoch stays
+    const int t0 = ctrl->t;
+    int trip = -1, reason = 0;
+    double v = 0.0;
+    for (int i = 0; i < count; ++i) {
+        v = chunkvol[i];
+        if (t0 + i < volumes_cap) volumes[t0 + i] = v;
+        if (spec && trip < 0) {
+            if (v >= stop_volume) { trip = i; reason = 1; }
+            else if (v < small_volume) { trip = i; reason = 2; }
+            if (trip >= 0) ctrl->last_volume = v;
+        }
+    }
+    flags[kSlabEpoch] += count;
+    if (trip >= 0) {
+        ctrl->stop_step = t0 + trip;
+        ctrl->replay = trip + 1;
+        __threadfence();
+        ctrl->stop_reason = reason;
+    } else {
+        ctrl->last_volume = v;
+        ctrl->t = t0 + count;
+        ctrl->replay = 0;
+    }
+}
+
 // speculative mode: the state before a chunk, kept until the chunk's stop tests have passed
+// (flags != nullptr, fused slab mode: the ghost planes are part of that state -- wait until both neighbours'
+// pushes of the previous launch have landed)
 __global__ void __launch_bounds__(256) checkpoint_kernel(const Ctrl *ctrl, const uint2 *s0, const uint2 *s1, const uint2 *s2,
-                                                         uint2 *d0, uint2 *d1, uint2 *d2, size_t n8)
+                                                         uint2 *d0, uint2 *d1, uint2 *d2, size_t n8, int *flags)
 {
     if (*(volatile const int *)&ctrl->stop_reason != 0) return;
+    if (flags) {
+        if (threadIdx.x == 0) slab_spin(flags, kSlabFromPrev, kSlabFromNext, flags[kSlabEpoch]);
+        __syncthreads();
+    }
     for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < n8; q += (size_t)gridDim.x * blockDim.x) {
         d0[q] = s0[q];
         if (s1) d1[q] = s1[q];

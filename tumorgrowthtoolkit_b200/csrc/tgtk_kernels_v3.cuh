@@ -295,8 +295,8 @@ __device__ __forceinline__ Stage2 stage2_setup(const StepArgs<T> &a, int lx)
     const int r0 = y0 + 2 * ty;
     g.valid0 = (z0 + tz < a.Z) && (r0 < a.Y);
     g.valid1 = (z0 + tz < a.Z) && (r0 + 1 < a.Y);
-    g.x0 = blockIdx.z * lx;
-    g.x1 = min(g.x0 + lx, a.X);
+    g.x0 = a.x_lo + blockIdx.z * lx;
+    g.x1 = min(g.x0 + lx, a.x_hi);
     g.sx = (uint32_t)a.sx;
     g.wrap_back = (uint32_t)(a.X - 1) * g.sx;
     const uint32_t sy = (uint32_t)a.sy, base = (uint32_t)g.x0 * g.sx;
@@ -341,6 +341,11 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> 
     double sP = 0.0, sN = 0.0;
     griddep_launch();
     griddep_wait();
+    const SlabCtl sl = slab_begin(a, g.x0, g.x1);
+    auto push = [&](T *const *peer, uint32_t off, T pn0, T nn0, T sn0, T pn1, T nn1, T sn1) {
+        if (g.valid0) { peer[0][g.c0 + off] = pn0; peer[1][g.c0 + off] = nn0; peer[2][g.c0 + off] = sn0; }
+        if (g.valid1) { peer[0][g.c1 + off] = pn1; peer[1][g.c1 + off] = nn1; peer[2][g.c1 + off] = sn1; }
+    };
 
     Vox2c<T> A0, A1, B0, B1;               // rows (y, y+1) of plane x (A) and plane x+1 (B); roles swap
     load(A0, g.c0); A0.k = keff(A0.p, A0.n, A0.k);
@@ -423,6 +428,8 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> 
             Po[g.c1] = pn1; No[g.c1] = nn1; So[g.c1] = sn1;
             if (cnt) { sP += (double)pn1; sN += (double)nn1; }
         }
+        if (sl.lo && x == a.x_lo) push(a.peer_lo[sc.par ^ 1], a.off_lo, pn0, nn0, sn0, pn1, nn1, sn1);
+        if (sl.hi && x == a.x_hi - 1) push(a.peer_hi[sc.par ^ 1], a.off_hi, pn0, nn0, sn0, pn1, nn1, sn1);
         fp_lo0 = fp_hi0; fs_lo0 = fs_hi0; fp_lo1 = fp_hi1; fs_lo1 = fs_hi1;
         g.c0 = n0; g.c1 = n1;
         buf ^= 1;
@@ -432,6 +439,7 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> 
         if (x + 1 >= g.x1) break;
         step(x + 1, B0, B1, A0, A1);
     }
+    slab_end(a, sl);
     step_end<T, 2>(a, sc, sP, sN);
 }
 
@@ -452,6 +460,11 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk_step_v4(const StepArgs<T> a,
     double s = 0.0;
     griddep_launch();
     griddep_wait();
+    const SlabCtl sl = slab_begin(a, g.x0, g.x1);
+    auto push = [&](T *const *peer, uint32_t off, T v0, T v1) {
+        if (g.valid0) peer[0][g.c0 + off] = v0;
+        if (g.valid1) peer[0][g.c1 + off] = v1;
+    };
 
     VoxFk<T> A0, A1, B0, B1;
     A0.u = u[g.c0]; A0.k = kc[g.c0];
@@ -495,6 +508,8 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk_step_v4(const StepArgs<T> a,
         const bool cnt = counts(a, x);
         if (g.valid0) { out[g.c0] = un0; if (cnt) s += (double)un0; }
         if (g.valid1) { out[g.c1] = un1; if (cnt) s += (double)un1; }
+        if (sl.lo && x == a.x_lo) push(a.peer_lo[sc.par ^ 1], a.off_lo, un0, un1);
+        if (sl.hi && x == a.x_hi - 1) push(a.peer_hi[sc.par ^ 1], a.off_hi, un0, un1);
         f_lo0 = f_hi0; f_lo1 = f_hi1;
         g.c0 = n0; g.c1 = n1;
         buf ^= 1;
@@ -504,6 +519,7 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk_step_v4(const StepArgs<T> a,
         if (x + 1 >= g.x1) break;
         step(x + 1, B0, B1, A0, A1);
     }
+    slab_end(a, sl);
     step_end<T, 1>(a, sc, s, 0.0);
 }
 
@@ -530,6 +546,11 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) dti_step_v4(const StepArgs<T> a
     VoxDti<T> A0, A1, B0, B1;
     griddep_launch();
     griddep_wait();
+    const SlabCtl sl = slab_begin(a, g.x0, g.x1);
+    auto push = [&](T *const *peer, uint32_t off, T v0, T v1) {
+        if (g.valid0) peer[0][g.c0 + off] = v0;
+        if (g.valid1) peer[0][g.c1 + off] = v1;
+    };
     load(A0, g.c0);
     load(A1, g.c1);
     T um0 = u[g.prev0], um1 = u[g.prev1];
@@ -569,6 +590,8 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) dti_step_v4(const StepArgs<T> a
         const bool cnt = counts(a, x);
         if (g.valid0) { out[g.c0] = un0; if (cnt) s += (double)un0; }
         if (g.valid1) { out[g.c1] = un1; if (cnt) s += (double)un1; }
+        if (sl.lo && x == a.x_lo) push(a.peer_lo[sc.par ^ 1], a.off_lo, un0, un1);
+        if (sl.hi && x == a.x_hi - 1) push(a.peer_hi[sc.par ^ 1], a.off_hi, un0, un1);
         um0 = c0.u; um1 = c1.u;
         g.c0 = n0; g.c1 = n1;
         buf ^= 1;
@@ -578,6 +601,7 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) dti_step_v4(const StepArgs<T> a
         if (x + 1 >= g.x1) break;
         step(x + 1, B0, B1, A0, A1);
     }
+    slab_end(a, sl);
     step_end<T, 1>(a, sc, s, 0.0);
 }
 

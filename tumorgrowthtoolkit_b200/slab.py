@@ -12,14 +12,17 @@ that exceed one GPU's useful working set, e.g. the 2x up-sampled 480x480x310 atl
     outermost ghost planes are stale, the owned planes never are (overlapped halo recompute).
     One exchange per `halo` steps amortises its latency, which for a 1/8 slab is longer than a
     step (SURVEY.md 7 "halo latency");
-  * the exchange is in place on the simulations' own device buffers, no staging copies.  Three
-    drivers: "p2p" (default) maps the neighbours' buffers with CUDA IPC and PUSHES the owned boundary
-    planes into their ghost planes over NVLink, fenced by epoch flags in peer memory -- no NCCL, the
-    whole block replayed from a CUDA graph; "native" enqueues grouped ncclSend/ncclRecv from C;
-    "torch" uses torch.distributed send/recv per block (NCCL on GPU tensors, gloo in the CPU tests);
-  * volumes are summed over owned planes only (tgtk_sim_set_sum_range) and all-reduced once.
-
-Only runs without a volume stop criterion are supported here (stopping_volume = inf).
+  * the exchange is in place on the simulations' own device buffers, no staging copies.  Four drivers:
+    "fused" (default, halo 1): the STEP KERNEL itself stores the rank's two boundary planes into the neighbours'
+    ghost planes (CUDA-IPC mapped peer memory, NVLink) and publishes an epoch word there; only the thread blocks
+    that read a ghost plane wait for the neighbour's previous epoch, interior blocks never do -- no exchange
+    launches, no ghost recompute, and the transfer of step t overlaps the interior of step t+1.  Stop criteria
+    (`stopping_volume`, FK_DTI's `volume < 1e-6`), snapshots and reset work as on one GPU: each chunk's volumes
+    are summed over the ranks with one small ncclAllReduce before the reference's stop tests run on them.
+    "p2p" maps the neighbours' buffers the same way and PUSHES the boundary planes with peer copies between
+    graph-replayed blocks of `halo` steps, fenced by epoch flags; "native" enqueues grouped ncclSend/ncclRecv
+    from C; "torch" uses torch.distributed send/recv per block (NCCL on GPU tensors, gloo in the CPU tests);
+  * volumes are summed over owned planes only and reduced over the ranks.
 """
 import numpy as np
 
@@ -202,87 +205,205 @@ def _native_comm(dist, rank, world, device):
     return _COMMS[key]
 
 
-def _run_cuda(model, fields_in, statics, scalars, shape, h, dt, nsteps, halo, precision, device, names, driver="p2p"):
-    import torch
-    from . import _native as nat
-    from ._loop import dtype_code
-    dist, rank, world = _dist()
-    plan = SlabPlan(shape[0], world, rank, halo)
-    local_shape = (plan.local_planes,) + tuple(shape[1:])
-    p = nat.make_params(model, dtype_code(precision), local_shape, h, dt, **scalars)
-    uploads = [(f, plan.extend(a)) for f, a in statics] + [(f, plan.extend(a)) for f, a in fields_in]
-    stepper = CudaSlabStepper(plan, p, uploads, [f for f, _ in fields_in], device, ipc=(driver == "p2p"))
-    # device time of the whole decomposed loop (step kernels + halo exchanges) on this rank
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stepper.tstream)
-    if driver == "p2p":
-        # peer-to-peer pushes over NVLink: map the neighbours' buffers (CUDA IPC handles travel over the
-        # caller's torch.distributed group), then the library enqueues steps + pushes + handshakes
-        mine = stepper.sim.ipc_export()
-        if world > 1:
-            t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(f"cuda:{device}")
-            allh = [torch.empty_like(t) for _ in range(world)]
-            dist.all_gather(allh, t)
-            hb = [bytes(h.cpu().numpy().tobytes()) for h in allh]
-            stepper.sim.ipc_connect(hb[plan.prev], hb[plan.next], same_peer=(plan.prev == plan.next))
-            dist.barrier()
+class SlabSession:
+    """One rank's share of a slab-decomposed solve, kept alive across runs (bench.py times repeated loops on it;
+    `_run_cuda` is create + one run + gather).  All ranks of the torch.distributed group construct it together."""
+
+    def __init__(self, model, fields_in, statics, scalars, shape, h, dt, halo, precision, device, names, driver="p2p"):
+        import torch
+        from . import _native as nat
+        from ._loop import dtype_code
+        self.torch, self.nat, self.driver, self.device, self.names = torch, nat, driver, device, names
+        self.dist, self.rank, self.world = _dist()
+        if driver == "fused" and halo != 1:
+            raise ValueError("the fused driver exchanges one plane per side every step: halo must be 1")
+        self.plan = plan = SlabPlan(shape[0], self.world, self.rank, halo)
+        local_shape = (plan.local_planes,) + tuple(shape[1:])
+        p = nat.make_params(model, dtype_code(precision), local_shape, h, dt, **scalars)
+        uploads = [(f, plan.extend(a)) for f, a in statics] + [(f, plan.extend(a)) for f, a in fields_in]
+        self.fields = [f for f, _ in fields_in]
+        self.stepper = CudaSlabStepper(plan, p, uploads, self.fields, device, ipc=(driver in ("p2p", "fused")))
+        self.sim = self.stepper.sim
+        self.ev0, self.ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.comm = None
+        if driver in ("p2p", "fused"):
+            # peer-to-peer pushes over NVLink: map the neighbours' buffers (CUDA IPC handles travel over the
+            # caller's torch.distributed group)
+            mine = self.sim.ipc_export()
+            if self.world > 1:
+                t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(f"cuda:{device}")
+                allh = [torch.empty_like(t) for _ in range(self.world)]
+                self.dist.all_gather(allh, t)
+                hb = [bytes(h.cpu().numpy().tobytes()) for h in allh]
+                self.sim.ipc_connect(hb[plan.prev], hb[plan.next], same_peer=(plan.prev == plan.next))
+            else:
+                self.sim.ipc_connect(None, None)
+            if driver == "fused":
+                # stop criteria need the global volume: one small NCCL all-reduce per chunk of steps
+                self.comm = _native_comm(self.dist, self.rank, self.world, device) if self.world > 1 else None
+                self.sim.slab_attach(self.comm, plan.n, plan.sizes[plan.prev])
+        elif driver == "native":
+            self.comm = _native_comm(self.dist, self.rank, self.world, device) if self.world > 1 else None
+        self._barrier()
+        self._torch_ms = 0.0
+
+    def _barrier(self):
+        self.stepper.tstream.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+
+    def reset(self):
+        """Back to the uploaded initial state (ghost planes included); collective."""
+        self.sim.reset()
+        self.stepper.steps = 0
+        self._barrier()
+
+    def run(self, nsteps, record_steps=None):
+        plan, sim = self.plan, self.sim
+        if record_steps is not None and self.driver != "fused":
+            raise ValueError("snapshots inside a decomposed run need driver='fused'")
+        if self.driver == "fused":
+            sim.run(nsteps, record_steps)                # tgtk_sim_run in slab mode: pushes and flag waits inside the step kernels
+            self.stepper.steps += nsteps
+        elif self.driver == "p2p":
+            sim.run_slab_p2p(nsteps, plan.halo, plan.n, plan.sizes[plan.prev])
+            self.stepper.steps += nsteps
+        elif self.driver == "native":
+            sim.run_slab(self.comm, nsteps, plan.halo, plan.n, plan.prev, plan.next)
+            self.stepper.steps += nsteps
         else:
-            stepper.sim.ipc_connect(None, None)
-        ev0.record(stepper.tstream)
-        stepper.sim.run_slab_p2p(nsteps, plan.halo, plan.n, plan.sizes[plan.prev])
-        stepper.steps = nsteps
-    elif driver == "native":
-        # the whole loop (steps + NCCL ring exchanges) enqueued by the library on the sim's stream
-        comm = _native_comm(dist, rank, world, device) if world > 1 else None
-        stepper.sim.run_slab(comm, nsteps, plan.halo, plan.n, plan.prev, plan.next)
-        stepper.steps = nsteps
-    else:
-        run_blocks(plan, stepper, nsteps, dist)       # torch.distributed send/recv per block
-    ev1.record(stepper.tstream)
-    if driver == "p2p":
-        stepper.tstream.synchronize()
-        err = stepper.sim.slab_error()
-        if world > 1:
-            dist.barrier()          # nobody unmaps buffers a neighbour may still be pushing into
-        if err:
-            raise nat.NativeError(f"peer-to-peer halo handshake {err} timed out (a neighbouring rank stalled)")
-    st, vols, owned = stepper.finish()
-    loop_ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        v = torch.from_numpy(vols).to(f"cuda:{device}")
-        dist.all_reduce(v)
-        vols = v.cpu().numpy()
-    state = {n: _gather_planes(plan, owned[f], dist, torch, device) for n, (f, _) in zip(names, fields_in)}
-    res = dict(state=state, volume=float(vols[-1]) if len(vols) else None, steps_run=int(nsteps), stop="time",
-               t_stop=None, snapshots=None, volumes=vols, loop_ms=float(loop_ms), plan=plan)
-    if len(names) == 1:
-        res["state"] = state[names[0]]
-    return res
+            self.ev0.record(self.stepper.tstream)
+            run_blocks(plan, self.stepper, nsteps, self.dist)       # torch.distributed send/recv per block
+            self.ev1.record(self.stepper.tstream)
+
+    def sync(self):
+        """Wait for the enqueued loop; returns the library's status (collective for the fused driver: a tripped
+        stop criterion is replayed from the checkpoint by all ranks in lockstep)."""
+        st = self.sim.sync()
+        if self.driver in ("p2p", "fused"):
+            err = self.sim.slab_error()
+            if err:
+                raise self.nat.NativeError(f"peer-to-peer halo handshake {err} timed out (a neighbouring rank stalled)")
+        self.status = st
+        return st
+
+    def sync_ms(self):
+        st = self.sync()
+        if self.driver == "torch":
+            self.stepper.tstream.synchronize()
+            return float(self.ev0.elapsed_time(self.ev1))
+        return float(st.loop_ms)
+
+    def launches(self):
+        return int(self.sim.sync().kernel_launches)
+
+    def volumes(self):
+        """Per-step volumes summed over ranks."""
+        torch = self.torch
+        st = self.sync()
+        vols = self.sim.volumes(0, st.steps_run)
+        if self.world > 1 and self.driver != "fused":      # the fused driver logs globally reduced volumes already
+            v = torch.from_numpy(vols).to(f"cuda:{self.device}")
+            self.dist.all_reduce(v)
+            vols = v.cpu().numpy()
+        return vols
+
+    def volume(self):
+        v = self.volumes()
+        return float(v[-1]) if len(v) else None
+
+    def gather(self, snapshot=None):
+        """The global state (or snapshot `snapshot`) on every rank: array, or {'P','N','S'}."""
+        self.sync()
+        out = {}
+        for n, f in zip(self.names, self.fields):
+            loc = self.sim.download(f) if snapshot is None else self.sim.snapshot(snapshot, f)
+            out[n] = _gather_planes(self.plan, loc[self.plan.owned], self.dist, self.torch, self.device)
+        return out[self.names[0]] if len(self.names) == 1 else out
+
+    def close(self):
+        if self.sim is not None:
+            self.stepper.tstream.synchronize()
+            if self.world > 1:
+                self.dist.barrier()      # nobody unmaps buffers a neighbour may still be pushing into
+            self.sim.close()
+            self.sim = None
 
 
-def fk_loop(u0, WM, GM, th, Dw, ratio, rho, dt, dx, dy, dz, nsteps, halo=4, precision="fp64", device=0, driver="p2p"):
+def _run_cuda(model, fields_in, statics, scalars, shape, h, dt, nsteps, halo, precision, device, names, driver="p2p",
+              record_steps=None):
+    sess = SlabSession(model, fields_in, statics, scalars, shape, h, dt, halo, precision, device, names, driver)
+    sess.run(nsteps, record_steps)
+    loop_ms = sess.sync_ms()
+    st = sess.status
+    vols = sess.volumes()
+    state = sess.gather()
+    snaps = None
+    if record_steps is not None:
+        per = [sess.gather(snapshot=i) for i in range(st.snapshots)]
+        snaps = per if len(names) == 1 else {n: [q[n] for q in per] for n in names}
+    sess.close()
+    nat = sess.nat
+    stop = {nat.STOP_NONE: "time", nat.STOP_VOLUME: "volume", nat.STOP_SMALL: "small"}[st.stop_reason]
+    steps_run = int(st.steps_run) if driver == "fused" else int(nsteps)
+    return dict(state=state, volume=float(vols[-1]) if len(vols) else None, steps_run=steps_run, stop=stop,
+                t_stop=(int(st.stop_step) if st.stop_reason == nat.STOP_VOLUME else None), snapshots=snaps, volumes=vols,
+                loop_ms=float(loop_ms), launches=int(st.kernel_launches), plan=sess.plan)
+
+
+def _scalars(stopping_volume=np.inf, small_volume=0.0, **kw):
+    if not np.isinf(stopping_volume):
+        kw["stopping_volume"] = stopping_volume
+    if small_volume:
+        kw["small_volume"] = small_volume
+    return kw
+
+
+def _stop_args(driver, stopping_volume, small_volume, record_steps):
+    if driver != "fused" and (not np.isinf(stopping_volume) or small_volume or record_steps is not None):
+        raise ValueError("stop criteria and snapshots inside a decomposed run need driver='fused'")
+
+
+def fk_loop(u0, WM, GM, th, Dw, ratio, rho, dt, dx, dy, dz, nsteps, halo=1, precision="fp64", device=0, driver="fused",
+            stopping_volume=np.inf, record_steps=None):
     """FK.py:200,212-226 on a slab-decomposed grid (all ranks pass the same global arrays)."""
     from . import _native as nat
+    _stop_args(driver, stopping_volume, 0.0, record_steps)
     return _run_cuda(nat.MODEL_FK, [(nat.FIELD_U, u0)], [(nat.FIELD_WM, WM), (nat.FIELD_GM, GM)],
-                     dict(rho=rho, Dw=Dw, ratio=ratio, th_matter=th), np.shape(u0), (dx, dy, dz), dt, nsteps, halo,
-                     precision, device, ("u",), driver)
+                     _scalars(stopping_volume, rho=rho, Dw=Dw, ratio=ratio, th_matter=th), np.shape(u0), (dx, dy, dz), dt, nsteps,
+                     halo, precision, device, ("u",), driver, record_steps)
 
 
-def dti_loop(u0, rgb, Dw, rho, dt, dx, dy, dz, nsteps, halo=4, precision="fp64", device=0, driver="p2p"):
-    """FK_DTI.py:174,195-214 on a slab-decomposed grid (without the `volume < 1e-6` exit)."""
+def _dti_args(u0, rgb, Dw, rho, stopping_volume, small_volume):
     from . import _native as nat
     rgb = np.asarray(rgb)
     statics = [(nat.FIELD_COEF0 + a, rgb[..., a] * Dw) for a in range(3)]
-    return _run_cuda(nat.MODEL_DTI, [(nat.FIELD_U, u0)], statics, dict(rho=rho, Dw=Dw), np.shape(u0), (dx, dy, dz), dt,
-                     nsteps, halo, precision, device, ("u",), driver)
+    return nat.MODEL_DTI, [(nat.FIELD_U, u0)], statics, _scalars(stopping_volume, small_volume, rho=rho, Dw=Dw)
+
+
+def dti_loop(u0, rgb, Dw, rho, dt, dx, dy, dz, nsteps, halo=1, precision="fp64", device=0, driver="fused",
+             stopping_volume=np.inf, small_volume=0.0, record_steps=None):
+    """FK_DTI.py:174,195-214 on a slab-decomposed grid.  small_volume=1e-6 enables the reference's
+    `volume < 1e-6` exit (FK_DTI.py:203-206; fused driver only)."""
+    _stop_args(driver, stopping_volume, small_volume, record_steps)
+    model, fields, statics, scalars = _dti_args(u0, rgb, Dw, rho, stopping_volume, small_volume)
+    return _run_cuda(model, fields, statics, scalars, np.shape(u0), (dx, dy, dz), dt, nsteps, halo, precision, device, ("u",),
+                     driver, record_steps)
+
+
+def session_dti(u0, rgb, Dw, rho, dt, dx, dy, dz, halo=1, precision="fp64", device=0, driver="fused"):
+    """A reusable decomposed FK_DTI problem (bench.py: reset / run / sync_ms repeatedly)."""
+    model, fields, statics, scalars = _dti_args(u0, rgb, Dw, rho, np.inf, 0.0)
+    return SlabSession(model, fields, statics, scalars, np.shape(u0), (dx, dy, dz), dt, halo, precision, device, ("u",), driver)
 
 
 def fk2c_loop(P0, N0, S0, WM, GM, th, th_necro, Dw, ratio, Ds, rho, lambda_np, sigma_np, lambda_s, dt, dx, dy, dz,
-              nsteps, halo=4, precision="fp64", device=0, driver="p2p"):
-    """FK_2c.py:215-216,227-245 on a slab-decomposed grid: P, N and S halos are exchanged."""
+              nsteps, halo=1, precision="fp64", device=0, driver="fused", stopping_volume=np.inf, record_steps=None):
+    """FK_2c.py:215-216,227-245 on a slab-decomposed grid: P, N and S boundary planes are exchanged."""
     from . import _native as nat
+    _stop_args(driver, stopping_volume, 0.0, record_steps)
     return _run_cuda(nat.MODEL_FK_2C, [(nat.FIELD_P, P0), (nat.FIELD_N, N0), (nat.FIELD_S, S0)],
                      [(nat.FIELD_WM, WM), (nat.FIELD_GM, GM)],
-                     dict(rho=rho, Dw=Dw, ratio=ratio, th_matter=th, th_necro=th_necro, Ds=Ds, lambda_np=lambda_np,
-                          sigma_np=sigma_np, lambda_s=lambda_s), np.shape(P0), (dx, dy, dz), dt, nsteps, halo,
-                     precision, device, ("P", "N", "S"), driver)
+                     _scalars(stopping_volume, rho=rho, Dw=Dw, ratio=ratio, th_matter=th, th_necro=th_necro, Ds=Ds,
+                              lambda_np=lambda_np, sigma_np=sigma_np, lambda_s=lambda_s), np.shape(P0), (dx, dy, dz), dt,
+                     nsteps, halo, precision, device, ("P", "N", "S"), driver, record_steps)

@@ -83,3 +83,39 @@ def dti_tensor_field(wm, gm, seed=20261019):
             T[..., a, b] = np.where(is_wm, aniso, 0.0)
         T[..., a, a] += np.where(is_gm, 1.0e-3, 0.0)
     return T
+
+
+def dti_lower6_field(seg, seed=20261019, sigma=6.0):
+    """SURVEY.md 8(d) input 3: synthetic (X,Y,Z,6) lower-triangular tensor volume
+    [dxx, dxy, dyy, dxz, dyz, dzz] (the storage TumorGrowthToolkit/FK_DTI/tools.py:91-106 unpacks) from a tissue
+    label volume (3 = WM, 2 = GM): isotropic 1e-3*I in GM, eigenvalues (1.7, 0.3, 0.3)e-3 along a smooth unit
+    direction field normalize(gaussian_filter(rng.normal(size=(3,)+shape), sigma)) in WM, zero in CSF and
+    background (what FK_DTI_example.ipynb cell 3 does with its mask).  Stands in for the FSL_HCP1065 tensor
+    volume, which the reference repository does not ship."""
+    from scipy.ndimage import gaussian_filter
+    seg = np.asarray(seg)
+    rng = np.random.default_rng(seed)
+    e = np.stack([gaussian_filter(rng.normal(size=seg.shape), sigma) for _ in range(3)])
+    nrm = np.sqrt((e * e).sum(axis=0))
+    nrm[nrm == 0] = 1.0
+    e /= nrm
+    is_wm, is_gm = seg == 3, seg == 2
+    out = np.zeros(seg.shape + (6,), dtype=np.float64)
+    for c, (a, b) in enumerate(((0, 0), (0, 1), (1, 1), (0, 2), (1, 2), (2, 2))):
+        aniso = 1.4e-3 * e[a] * e[b] + (0.3e-3 if a == b else 0.0)
+        out[..., c] = np.where(is_wm, aniso, 0.0)
+        if a == b:
+            out[..., c] += np.where(is_gm, 1.0e-3, 0.0)
+    return out
+
+
+def seed_inside(mask, pct):
+    """Seed fractions for FK_DTI_Solver (NxT1_pct, ...): `pct` itself when int(pct*n) lands inside `mask`, else the
+    fractions of the mask voxel nearest to it (SURVEY.md 8(d) input 3: "re-pick inside WM if outside")."""
+    shape = np.array(mask.shape)
+    idx = tuple(int(p * n) for p, n in zip(pct, shape))
+    if mask[idx]:
+        return tuple(float(p) for p in pct)
+    cand = np.argwhere(mask)
+    best = cand[np.argmin(((cand - np.array(idx)) ** 2).sum(axis=1))]
+    return tuple(float((b + 0.5) / n) for b, n in zip(best, shape))
