@@ -670,12 +670,12 @@ def main():
         dev_ms = sum(one_step() for _ in range(args.steps))
         barrier()
         wall = time.perf_counter() - t0
+        launches = int(sim.sync().kernel_launches - launches0) * args.steps // (args.warmup + args.steps)
         if wall < 0.6:                          # too short for a 200 ms sampler: keep the GPU under the same
             t1 = time.perf_counter()            # load (untimed) until a few samples exist
             while time.perf_counter() - t1 < 0.8:
                 one_step()
     st = sim.sync()
-    launches = int(st.kernel_launches - launches0) // (args.warmup + args.steps) * args.steps
     final_volume = st.last_volume
 
     # ---- end-to-end arm: host buffers through the C ABI ------------------------------------
