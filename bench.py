@@ -471,39 +471,53 @@ def ensemble_leg(args, rank, world, device, dist):
             "sharding": "sorted by step count, dealt round-robin; no data-path collective"}
 
 
-def slab_leg(args, rank, world, device, dist, pb):
-    """BASELINE.json configs[4]: returns (value GLUPS, ms per bench step, slab object, e2e object, launches)."""
+def slab_session(args, pb, device):
+    from tumorgrowthtoolkit_b200 import slab
+    q, h, f = pb["q"], pb["h"], pb["fields"]
+    kw = dict(halo=args.slab_halo, precision=args.precision, device=device, driver=args.slab_driver)
+    if pb["model"] == "dti":
+        return slab.session_dti(f["u"], f["rgb"], q["Dw"], q["rho"], pb["dt"], *h, **kw)
+    return slab.session_fk2c(f["P"], f["N"], f["S"], pb["wm"], pb["gm"], q["th_matter"], q["th_necro"], q["Dw"], q["ratio"], q["D_s"],
+                             q["rho"], q["lambda_np"], q["sigma_np"], q["lambda_s"], pb["dt"], *h, **kw)
+
+
+def slab_leg(args, rank, world, device, dist, pb, steps, warmup, with_e2e=True):
+    """BASELINE.json configs[4] for one model: (value GLUPS, ms per bench step, slab object, e2e object, launches, clocks, wall)."""
     import torch
-    from tumorgrowthtoolkit_b200 import _loop, slab
+    from tumorgrowthtoolkit_b200 import slab, _native as nat
     q, h, f = pb["q"], pb["h"], pb["fields"]
     nsteps = args.slab_steps
-    sess = slab.session_dti(f["u"], f["rgb"], q["Dw"], q["rho"], pb["dt"], *h, halo=args.slab_halo, precision=args.precision,
-                            device=device, driver=args.slab_driver)
+    names = "PNS" if pb["model"] == "fk2c" else ("u",)
+    sess = slab_session(args, pb, device)
 
     def one_step():
         sess.reset()
-        if dist is not None:
-            dist.barrier()
         sess.run(nsteps)
         return sess.sync_ms()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         one_step()
     launches0 = sess.launches()
     with ClockSampler(device) as clocks:
         t0 = time.perf_counter()
-        ms = sum(one_step() for _ in range(args.steps))
+        ms = sum(one_step() for _ in range(steps))
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
         wall = time.perf_counter() - t0
-    launches = sess.launches() - launches0
-    # parity: 13 steps of the decomposed loop against the undecomposed loop on rank 0's GPU, every voxel compared
+        launches = sess.launches() - launches0
+        extra = int(np.ceil(max(0.0, 0.8 - wall) / max(wall / steps, 1e-3)))      # same on every rank: wall was barrier-aligned ...
+        if dist is not None:                                                       # ... but make sure of it
+            te = torch.tensor([extra], device=f"cuda:{device}")
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            extra = int(te[0])
+        for _ in range(extra):                  # too short for a 200 ms sampler: keep the same load on (untimed) until samples exist
+            one_step()
+    # parity: 13 steps of the decomposed loop against the undecomposed loop on rank 0's GPU, every field, every voxel
     sess.reset()
-    if dist is not None:
-        dist.barrier()
     sess.run(13)
     got = sess.gather()
+    got = got if isinstance(got, dict) else {"u": got}
     vol13 = sess.volume()
     sess.close()
     t = torch.tensor([ms, wall, float(launches)], dtype=torch.float64, device=f"cuda:{device}")
@@ -513,25 +527,24 @@ def slab_leg(args, rank, world, device, dist, pb):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         ms, wall = float(tm[0]), float(tm[1])
     launches = int(round(float(t[2])))
-    updates = float(pb["voxels"]) * nsteps * args.steps
+    updates = float(pb["voxels"]) * nsteps * steps
     value = updates / (ms * 1e-3) / 1e9
-    info = {"workload": f"FK_DTI {int(240 * pb['res'])}x{int(240 * pb['res'])}x{int(155 * pb['res'])} -> cropped {pb['shape'][0]}x{pb['shape'][1]}x{pb['shape'][2]}, "
-                        f"{nsteps} time steps", "driver": args.slab_driver, "halo": args.slab_halo, "glups": value,
-            "loop_ms_max_over_ranks": ms / args.steps, "planes_per_rank": [int(v) for v in sess.plan.sizes]}
-    e2e = None
+    info = {"workload": f"{pb['model']} {int(240 * pb['res'])}x{int(240 * pb['res'])}x{int(155 * pb['res'])} -> cropped "
+                        f"{pb['shape'][0]}x{pb['shape'][1]}x{pb['shape'][2]}, {nsteps} time steps", "driver": args.slab_driver,
+            "halo": args.slab_halo, "glups": value, "loop_ms_max_over_ranks": ms / steps, "us_per_time_step": 1e3 * ms / steps / nsteps,
+            "planes_per_rank": [int(v) for v in sess.plan.sizes]}
     if rank == 0:
         # the same grid undecomposed on one GPU: speed-up denominator and parity reference
-        sim, _ = make_sim(pb, args.precision, device)
+        sim, out_fields = make_sim(pb, args.precision, device)
         tun = sim.tuning()
         sim.run(13)
-        sim.sync()
-        from tumorgrowthtoolkit_b200 import _native as nat
-        ref = sim.download(nat.FIELD_U)
-        info["max_abs_diff_vs_undecomposed"] = float(np.max(np.abs(got - ref)))
+        st13 = sim.sync()
+        ref = {k: sim.download(fld) for k, fld in zip(names, out_fields)}
+        info["max_abs_diff_vs_undecomposed"] = max(float(np.max(np.abs(got[k] - ref[k]))) for k in names)
         info["parity_steps"] = 13
-        info["volume_rel_diff"] = abs(vol13 - sim.sync().last_volume) / abs(sim.sync().last_volume)
+        info["volume_rel_diff"] = abs(vol13 - st13.last_volume) / abs(st13.last_volume)
         best = 1e30
-        for _ in range(max(2, args.warmup)):
+        for _ in range(max(2, warmup)):
             sim.reset()
             sim.run(nsteps)
             best = min(best, sim.sync().loop_ms)
@@ -539,31 +552,29 @@ def slab_leg(args, rank, world, device, dist, pb):
         info["one_gpu_loop_ms"] = best
         info["one_gpu_glups"] = pb["voxels"] * nsteps / (best * 1e-3) / 1e9
         info["one_gpu_steps_per_launch"] = tun["steps_per_launch"]
-        info["speedup_vs_1gpu"] = best / (ms / args.steps)
+        info["speedup_vs_1gpu"] = best / (ms / steps)
         info["efficiency_vs_1gpu"] = info["speedup_vs_1gpu"] / world
-        info["exchange_us"] = None
     if dist is not None:
         dist.barrier()
-    # end to end: the public slab API on host arrays (create, upload of the extended slabs, the whole-length loop, download + gather)
-    t0 = time.perf_counter()
-    res = slab.dti_loop(f["u"], f["rgb"], q["Dw"], q["rho"], pb["dt"], *h, pb["nsteps"], halo=args.slab_halo, precision=args.precision,
-                        device=device, driver=args.slab_driver)
-    torch.cuda.synchronize()
-    e2e_wall = time.perf_counter() - t0
-    t = torch.tensor([e2e_wall], dtype=torch.float64, device=f"cuda:{device}")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_wall = float(t[0])
-    plan = res["plan"]
-    esz = 8
-    per_rank_planes = plan.local_planes
-    plane_bytes = pb["shape"][1] * pb["shape"][2] * esz
-    e2e = {"value": pb["voxels"] * pb["nsteps"] / e2e_wall / 1e9, "unit": "GLUPS",
-           "h2d_bytes_per_step": int(4 * per_rank_planes * plane_bytes * world), "d2h_bytes_per_step": int(pb["voxels"] * esz),
-           "ms_per_step": 1e3 * e2e_wall, "time_steps": pb["nsteps"],
-           "what": "slab.dti_loop on host arrays: sim create, H2D of every rank's extended slab (u + 3 coefficient arrays), the "
-                   "full-length decomposed loop, D2H of the owned planes, all-gather"}
-    return value, ms / args.steps, info, e2e, launches, clocks.summary(), wall
+    e2e = None
+    if with_e2e:
+        # end to end: the public slab API on host arrays (create, upload of the extended slabs, the whole-length loop, download + gather)
+        t0 = time.perf_counter()
+        res = slab.dti_loop(f["u"], f["rgb"], q["Dw"], q["rho"], pb["dt"], *h, pb["nsteps"], halo=args.slab_halo, precision=args.precision,
+                            device=device, driver=args.slab_driver)
+        torch.cuda.synchronize()
+        e2e_wall = time.perf_counter() - t0
+        t = torch.tensor([e2e_wall], dtype=torch.float64, device=f"cuda:{device}")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_wall = float(t[0])
+        plane_bytes = pb["shape"][1] * pb["shape"][2] * 8
+        e2e = {"value": pb["voxels"] * pb["nsteps"] / e2e_wall / 1e9, "unit": "GLUPS",
+               "h2d_bytes_per_step": int(4 * res["plan"].local_planes * plane_bytes * world), "d2h_bytes_per_step": int(pb["voxels"] * 8),
+               "ms_per_step": 1e3 * e2e_wall, "time_steps": pb["nsteps"],
+               "what": "slab.dti_loop on host arrays: sim create, H2D of every rank's extended slab (u + 3 coefficient arrays), the "
+                       "full-length decomposed loop, D2H of the owned planes, all-gather"}
+    return value, ms / steps, info, e2e, launches, clocks.summary(), wall
 
 
 # ------------------------------------------------------------------------------------------
@@ -618,7 +629,11 @@ def main():
         if args.slab_driver != "fused" and args.slab_halo == 1:
             args.slab_halo = 4
         pb = build_problem("dti", res=args.slab_res, on_gpu=True, device=device)
-        value, ms_step, info, e2e, launches, clocks, wall = slab_leg(args, rank, world, device, dist, pb)
+        value, ms_step, info, e2e, launches, clocks, wall = slab_leg(args, rank, world, device, dist, pb, args.steps, args.warmup)
+        # the same decomposition for FK_2c (P, N and S planes exchanged), a shorter measurement beside the headline
+        pb2 = build_problem("fk2c", res=args.slab_res, on_gpu=True, device=device)
+        _, _, info2, _, _, _, _ = slab_leg(args, rank, world, device, dist, pb2, max(1, args.steps // 2), 1, with_e2e=False)
+        del pb2
         ens = ensemble_leg(args, rank, world, device, dist) if args.patients > 0 else None
         if rank == 0:
             bpu = ALGO_BYTES[("dti", args.precision)]
@@ -636,7 +651,7 @@ def main():
                              "kernel": "dti_step_v4 (+ in-kernel halo push)" if args.slab_driver == "fused" else "dti_step",
                              "note": "per GPU: one rank's owned planes x algorithmic bytes / the step's share of the decomposed loop "
                                      "(exchange and synchronisation included)"},
-                "clocks": clocks, "wall_s_timed_region": wall, "slab": info, "ensemble": ens,
+                "clocks": clocks, "wall_s_timed_region": wall, "slab": info, "slab_fk2c": info2, "ensemble": ens,
                 "note": "N = 1 of this bench is BASELINE.json configs[1] (FK_2c, one GPU); N > 1 is configs[4] (this line) + configs[3] "
                         "(`ensemble`): compare N > 1 values with slab.one_gpu_glups, not with the N = 1 line",
             }

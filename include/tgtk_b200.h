@@ -169,10 +169,13 @@ int tgtk_sim_run_slab_p2p(tgtk_sim *sim, int nsteps, int halo, int owned, int pr
  * steps planes [1, 1 + owned) only; the blocks of the STEP KERNEL that compute a boundary plane also store it into the
  * neighbouring rank's ghost plane (peer-mapped memory over NVLink) and publish the launch's epoch in the neighbour's
  * flag word, the blocks that read a ghost plane wait for the neighbour's previous epoch -- no exchange launches, no
- * copies between steps, interior blocks never wait.  Per chunk of steps the volumes are summed over the ranks
+ * copies between steps, interior blocks never wait.  The lower half of the plane segments marches upwards and the upper
+ * half downwards, so both boundary planes leave at the START of a step.  When a stop criterion is active
+ * (stopping_volume / small_volume) the volumes of each chunk of steps are summed over the ranks
  * (ncclAllReduce on `comm`; NULL: one rank) before the reference's stop tests (FK/FK.py:216-218,
  * FK_DTI/FK_DTI.py:199-206) run on them, so stopping_volume, the `volume < 1e-6` exit, snapshots and tgtk_sim_reset
- * work as on one GPU.  All ranks must issue the same run / sync / reset sequence. */
+ * work as on one GPU; without one tgtk_sim_volumes returns the rank's own sums.  All ranks must issue the same
+ * run / sync / reset sequence. */
 int tgtk_sim_slab_attach(tgtk_sim *sim, void *comm, int owned, int prev_owned);
 /* 0, or which handshake timed out (p2p driver: 1 block done, 2 ghosts pushed; fused driver: 3). */
 int tgtk_sim_slab_error(tgtk_sim *sim, int *err);

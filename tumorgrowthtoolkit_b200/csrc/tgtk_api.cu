@@ -647,7 +647,10 @@ static int configure_launch(tgtk_sim *s)
         const double slots = (double)sms * per_sm;
         int best_lx = NX;
         double best_eff = -1.0;
-        for (int lx = 1; lx <= NX; ++lx) {
+        // fused slab mode: at least two segments, so that the lower one marches up and the upper one down and both
+        // boundary planes are pushed to the neighbours at the start of the step
+        const int lx_max = (s->slab_on && NX >= 2) ? (NX + 1) / 2 : NX;
+        for (int lx = 1; lx <= lx_max; ++lx) {
             const int ns = (NX + lx - 1) / lx;
             const double waves = tiles * (double)ns / slots;
             const double eff = waves / std::ceil(waves) * (lx / (lx + 0.6)) * ((double)NX / ((double)ns * lx));
@@ -829,8 +832,10 @@ static cudaError_t launch_chunk_finish(tgtk_sim *s, int count)
     s->chunk_tb_mask = 0;
     cudaError_t e = cudaGetLastError();
     if (!s->slab_on || e != cudaSuccess) return e;
-    // fused slab mode: sum the chunk's volumes over the ranks, then log them, run the stop tests, advance the counters
-    e = slab_allreduce(s, count);
+    // fused slab mode: sum the chunk's volumes over the ranks (only a stop criterion needs them during the loop; otherwise
+    // the log keeps the rank's own sums and the caller reduces it once at the end), then log them, run the stop tests,
+    // advance the counters
+    if (s->spec) e = slab_allreduce(s, count);
     if (e != cudaSuccess) return e;
     ++s->aux_launches;
     chunk_commit_kernel<<<1, 32, 0, s->stream>>>(s->ctrl, s->chunkvol, s->volumes, s->volumes_cap, count, spec, p.stopping_volume,

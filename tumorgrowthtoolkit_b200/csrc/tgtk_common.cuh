@@ -125,22 +125,21 @@ template <typename T> __device__ __forceinline__ SlabCtl slab_begin(const StepAr
     return c;
 }
 
-// after the last plane of the block: its pushes are made visible system-wide, the last block of each side publishes the epoch
-template <typename T> __device__ __forceinline__ void slab_end(const StepArgs<T> &a, const SlabCtl &c)
+// right after a block has stored a boundary plane into the neighbour's ghost plane (side 0: lowest owned plane ->
+// previous rank, 1: highest -> next rank): the stores are made visible system-wide and the LAST block of that side
+// publishes the launch's epoch in the neighbour's flag word.  By then every block of the side has also consumed its
+// own ghost plane of the buffer this launch reads (its result depends on it), so the neighbour may overwrite it.
+// Block-uniform; contains a __syncthreads().
+template <typename T> __device__ __forceinline__ void slab_signal(const StepArgs<T> &a, const SlabCtl &c, int side)
 {
-    if (!(c.lo || c.hi)) return;
     __syncthreads();
     if (threadIdx.x == 0 && threadIdx.y == 0) {
         __threadfence_system();
-        if (c.lo && atomicAdd((unsigned *)(a.flags + kSlabTicketLo), 1u) == a.ntiles - 1) {
-            a.flags[kSlabTicketLo] = 0;
+        int *ticket = a.flags + (side ? kSlabTicketHi : kSlabTicketLo);
+        if (atomicAdd((unsigned *)ticket, 1u) == a.ntiles - 1) {
+            *ticket = 0;
             __threadfence_system();
-            st_release_sys(a.flag_lo, c.epoch);
-        }
-        if (c.hi && atomicAdd((unsigned *)(a.flags + kSlabTicketHi), 1u) == a.ntiles - 1) {
-            a.flags[kSlabTicketHi] = 0;
-            __threadfence_system();
-            st_release_sys(a.flag_hi, c.epoch);
+            st_release_sys(side ? a.flag_hi : a.flag_lo, c.epoch);
         }
     }
 }
@@ -179,11 +178,12 @@ template <typename T> __device__ __forceinline__ L2Strip l2_strip_setup(const St
     s.total = (uint32_t)a.X * (uint32_t)a.sx;
     return s;
 }
-// element offset of the strip in plane x + l2pf (periodic)
-template <typename T> __device__ __forceinline__ uint32_t l2_strip_at(const StepArgs<T> &a, const L2Strip &s, int x)
+// element offset of the strip in plane x + l2pf (periodic); dir = -1: the block marches downwards, plane x - l2pf
+template <typename T> __device__ __forceinline__ uint32_t l2_strip_at(const StepArgs<T> &a, const L2Strip &s, int x, int dir = 1)
 {
-    int xp = x + a.l2pf;
+    int xp = x + dir * a.l2pf;
     if (xp >= a.X) xp -= a.X;
+    if (xp < 0) xp += a.X;
     return (uint32_t)xp * s.plane + s.row0;
 }
 

@@ -317,6 +317,41 @@ __device__ __forceinline__ Stage2 stage2_setup(const StepArgs<T> &a, int lx)
     return g;
 }
 
+// Marching direction of a block.  Fused slab mode: the segments of the upper half of the rank's planes march
+// DOWNWARDS, so that both boundary planes of the rank are computed -- and pushed to the neighbours -- at the very
+// start of the step and their epochs arrive long before the neighbours' next step needs them.  The face fluxes are
+// antisymmetric and the sums commutative, so a voxel's result does not depend on the direction (bitwise).
+struct March2 {
+    bool down;
+    int xs, dx, n;            // first plane, +-1, number of planes
+    uint32_t dsx;             // +-sx modulo 2^32
+    int wrapx;                // plane index after which the offset wraps back (upward marching over the whole box)
+    uint32_t wrapd;
+};
+
+template <typename T> __device__ __forceinline__ March2 march2_setup(const StepArgs<T> &a, Stage2 &g)
+{
+    March2 m;
+    m.down = a.slab && gridDim.z > 1 && 2 * blockIdx.z >= gridDim.z;
+    m.n = g.x1 - g.x0;
+    m.xs = g.x0;
+    m.dx = 1;
+    m.dsx = g.sx;
+    m.wrapx = a.X;
+    m.wrapd = 0u - g.wrap_back;
+    if (m.down) {             // start at the segment's top plane; "previous" is the plane above (never wraps: ghosts exist)
+        const uint32_t up = (uint32_t)(m.n - 1) * g.sx;
+        g.c0 += up; g.c1 += up; g.h += up;
+        g.prev0 = g.c0 + g.sx; g.prev1 = g.c1 + g.sx;
+        m.xs = g.x1 - 1;
+        m.dx = -1;
+        m.dsx = 0u - g.sx;
+        m.wrapx = -2;
+        m.wrapd = m.dsx;
+    }
+    return m;
+}
+
 template <typename T> struct Vox2c { T p, n, s, b, k; };
 
 template <typename T, int TZ, int TYT, int MINB = 2>
@@ -335,6 +370,7 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> 
     const T *__restrict__ kc = a.coef[0];
     const T *__restrict__ bc = a.coef[1];
     Stage2 g = stage2_setup<T, TZ, TYT, RS>(a, lx);
+    const March2 mm = march2_setup(a, g);
     const T closed = -Big<T>::v;
     auto keff = [&](T pq, T nq, T kq) { return (pq + nq <= a.th_necro) ? kq : closed; };
     auto load = [&](Vox2c<T> &v, uint32_t off) { v.p = P[off]; v.n = N[off]; v.s = S[off]; v.b = bc[off]; v.k = kc[off]; };
@@ -374,15 +410,15 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> 
             tl[0][g.hs] = Pair<T>{hp, keff(hp, hn, hk)};
             tl[1][g.hs] = Pair<T>{hsv, hb};
         }
-        // request plane x+1: both own voxels and the ring
-        const uint32_t n0 = (x + 1 == a.X) ? g.c0 - g.wrap_back : g.c0 + g.sx;
-        const uint32_t n1 = (x + 1 == a.X) ? g.c1 - g.wrap_back : g.c1 + g.sx;
+        // request the next plane of the march: both own voxels and the ring
+        const uint32_t adv = (x + 1 == mm.wrapx) ? mm.wrapd : mm.dsx;
+        const uint32_t n0 = g.c0 + adv, n1 = g.c1 + adv;
         load(p0, n0);
         load(p1, n1);
-        g.h = (x + 1 == a.X) ? g.h - g.wrap_back : g.h + g.sx;
+        g.h += adv;
         if (g.ring) { hp = P[g.h]; hn = N[g.h]; hk = kc[g.h]; hsv = S[g.h]; hb = bc[g.h]; }
         if (pf.on) {                           // this tile strip of plane x + l2pf into L2
-            const uint32_t q = l2_strip_at(a, pf, x);
+            const uint32_t q = l2_strip_at(a, pf, x, mm.dx);
             l2_prefetch_strip(P, q, pf.count, pf.total); l2_prefetch_strip(N, q, pf.count, pf.total);
             l2_prefetch_strip(S, q, pf.count, pf.total); l2_prefetch_strip(kc, q, pf.count, pf.total);
             l2_prefetch_strip(bc, q, pf.count, pf.total);
@@ -428,18 +464,17 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> 
             Po[g.c1] = pn1; No[g.c1] = nn1; So[g.c1] = sn1;
             if (cnt) { sP += (double)pn1; sN += (double)nn1; }
         }
-        if (sl.lo && x == a.x_lo) push(a.peer_lo[sc.par ^ 1], a.off_lo, pn0, nn0, sn0, pn1, nn1, sn1);
-        if (sl.hi && x == a.x_hi - 1) push(a.peer_hi[sc.par ^ 1], a.off_hi, pn0, nn0, sn0, pn1, nn1, sn1);
+        if (sl.lo && x == a.x_lo) { push(a.peer_lo[sc.par ^ 1], a.off_lo, pn0, nn0, sn0, pn1, nn1, sn1); slab_signal(a, sl, 0); }
+        if (sl.hi && x == a.x_hi - 1) { push(a.peer_hi[sc.par ^ 1], a.off_hi, pn0, nn0, sn0, pn1, nn1, sn1); slab_signal(a, sl, 1); }
         fp_lo0 = fp_hi0; fs_lo0 = fs_hi0; fp_lo1 = fp_hi1; fs_lo1 = fs_hi1;
         g.c0 = n0; g.c1 = n1;
         buf ^= 1;
     };
-    for (int x = g.x0; x < g.x1; x += 2) {
-        step(x, A0, A1, B0, B1);
-        if (x + 1 >= g.x1) break;
-        step(x + 1, B0, B1, A0, A1);
+    for (int i = 0; i < mm.n; i += 2) {
+        step(mm.xs + i * mm.dx, A0, A1, B0, B1);
+        if (i + 1 >= mm.n) break;
+        step(mm.xs + (i + 1) * mm.dx, B0, B1, A0, A1);
     }
-    slab_end(a, sl);
     step_end<T, 2>(a, sc, sP, sN);
 }
 
@@ -457,6 +492,7 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk_step_v4(const StepArgs<T> a,
     T *__restrict__ out = a.buf[sc.par ^ 1][0];
     const T *__restrict__ kc = a.coef[0];
     Stage2 g = stage2_setup<T, TZ, TYT, RS>(a, lx);
+    const March2 mm = march2_setup(a, g);
     double s = 0.0;
     griddep_launch();
     griddep_wait();
@@ -482,14 +518,14 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk_step_v4(const StepArgs<T> a,
         tl[o0] = Pair<T>{c0.u, c0.k};
         tl[o1] = Pair<T>{c1.u, c1.k};
         if (g.ring) tl[g.hs] = Pair<T>{hu, hk};
-        const uint32_t n0 = (x + 1 == a.X) ? g.c0 - g.wrap_back : g.c0 + g.sx;
-        const uint32_t n1 = (x + 1 == a.X) ? g.c1 - g.wrap_back : g.c1 + g.sx;
+        const uint32_t adv = (x + 1 == mm.wrapx) ? mm.wrapd : mm.dsx;
+        const uint32_t n0 = g.c0 + adv, n1 = g.c1 + adv;
         p0.u = u[n0]; p0.k = kc[n0];
         p1.u = u[n1]; p1.k = kc[n1];
-        g.h = (x + 1 == a.X) ? g.h - g.wrap_back : g.h + g.sx;
+        g.h += adv;
         if (g.ring) { hu = u[g.h]; hk = kc[g.h]; }
         if (pf.on) {
-            const uint32_t q = l2_strip_at(a, pf, x);
+            const uint32_t q = l2_strip_at(a, pf, x, mm.dx);
             l2_prefetch_strip(u, q, pf.count, pf.total); l2_prefetch_strip(kc, q, pf.count, pf.total);
         }
         const T react0 = a.rho * c0.u * (T(1) - c0.u), react1 = a.rho * c1.u * (T(1) - c1.u);
@@ -508,18 +544,17 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk_step_v4(const StepArgs<T> a,
         const bool cnt = counts(a, x);
         if (g.valid0) { out[g.c0] = un0; if (cnt) s += (double)un0; }
         if (g.valid1) { out[g.c1] = un1; if (cnt) s += (double)un1; }
-        if (sl.lo && x == a.x_lo) push(a.peer_lo[sc.par ^ 1], a.off_lo, un0, un1);
-        if (sl.hi && x == a.x_hi - 1) push(a.peer_hi[sc.par ^ 1], a.off_hi, un0, un1);
+        if (sl.lo && x == a.x_lo) { push(a.peer_lo[sc.par ^ 1], a.off_lo, un0, un1); slab_signal(a, sl, 0); }
+        if (sl.hi && x == a.x_hi - 1) { push(a.peer_hi[sc.par ^ 1], a.off_hi, un0, un1); slab_signal(a, sl, 1); }
         f_lo0 = f_hi0; f_lo1 = f_hi1;
         g.c0 = n0; g.c1 = n1;
         buf ^= 1;
     };
-    for (int x = g.x0; x < g.x1; x += 2) {
-        step(x, A0, A1, B0, B1);
-        if (x + 1 >= g.x1) break;
-        step(x + 1, B0, B1, A0, A1);
+    for (int i = 0; i < mm.n; i += 2) {
+        step(mm.xs + i * mm.dx, A0, A1, B0, B1);
+        if (i + 1 >= mm.n) break;
+        step(mm.xs + (i + 1) * mm.dx, B0, B1, A0, A1);
     }
-    slab_end(a, sl);
     step_end<T, 1>(a, sc, s, 0.0);
 }
 
@@ -540,6 +575,7 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) dti_step_v4(const StepArgs<T> a
     const T *__restrict__ dya = a.coef[1];
     const T *__restrict__ dza = a.coef[2];
     Stage2 g = stage2_setup<T, TZ, TYT, RS>(a, lx);
+    const March2 mm = march2_setup(a, g);
     double s = 0.0;
     auto load = [&](VoxDti<T> &v, uint32_t off) { v.u = u[off]; v.d0 = dxa[off]; v.d1 = dya[off]; v.d2 = dza[off]; };
 
@@ -573,35 +609,35 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) dti_step_v4(const StepArgs<T> a
         tl[o0] = c0.u;
         tl[o1] = c1.u;
         if (g.ring) tl[g.hs] = hu;
-        const uint32_t n0 = (x + 1 == a.X) ? g.c0 - g.wrap_back : g.c0 + g.sx;
-        const uint32_t n1 = (x + 1 == a.X) ? g.c1 - g.wrap_back : g.c1 + g.sx;
+        const uint32_t adv = (x + 1 == mm.wrapx) ? mm.wrapd : mm.dsx;
+        const uint32_t n0 = g.c0 + adv, n1 = g.c1 + adv;
         load(p0, n0);
         load(p1, n1);
-        g.h = (x + 1 == a.X) ? g.h - g.wrap_back : g.h + g.sx;
+        g.h += adv;
         if (g.ring) hu = u[g.h];
         if (pf.on) {
-            const uint32_t q = l2_strip_at(a, pf, x);
+            const uint32_t q = l2_strip_at(a, pf, x, mm.dx);
             l2_prefetch_strip(u, q, pf.count, pf.total); l2_prefetch_strip(dxa, q, pf.count, pf.total);
             l2_prefetch_strip(dya, q, pf.count, pf.total); l2_prefetch_strip(dza, q, pf.count, pf.total);
         }
         __syncthreads();
-        const T un0 = one(c0, um0, p0.u, tl[o0 - RS], c1.u, tl[o0 - 1], tl[o0 + 1]);
-        const T un1 = one(c1, um1, p1.u, c0.u, tl[o1 + RS], tl[o1 - 1], tl[o1 + 1]);
+        // um* = the plane behind the march, p*.u the plane ahead: x-1 / x+1 when marching up, swapped when marching down
+        const T un0 = one(c0, mm.down ? p0.u : um0, mm.down ? um0 : p0.u, tl[o0 - RS], c1.u, tl[o0 - 1], tl[o0 + 1]);
+        const T un1 = one(c1, mm.down ? p1.u : um1, mm.down ? um1 : p1.u, c0.u, tl[o1 + RS], tl[o1 - 1], tl[o1 + 1]);
         const bool cnt = counts(a, x);
         if (g.valid0) { out[g.c0] = un0; if (cnt) s += (double)un0; }
         if (g.valid1) { out[g.c1] = un1; if (cnt) s += (double)un1; }
-        if (sl.lo && x == a.x_lo) push(a.peer_lo[sc.par ^ 1], a.off_lo, un0, un1);
-        if (sl.hi && x == a.x_hi - 1) push(a.peer_hi[sc.par ^ 1], a.off_hi, un0, un1);
+        if (sl.lo && x == a.x_lo) { push(a.peer_lo[sc.par ^ 1], a.off_lo, un0, un1); slab_signal(a, sl, 0); }
+        if (sl.hi && x == a.x_hi - 1) { push(a.peer_hi[sc.par ^ 1], a.off_hi, un0, un1); slab_signal(a, sl, 1); }
         um0 = c0.u; um1 = c1.u;
         g.c0 = n0; g.c1 = n1;
         buf ^= 1;
     };
-    for (int x = g.x0; x < g.x1; x += 2) {
-        step(x, A0, A1, B0, B1);
-        if (x + 1 >= g.x1) break;
-        step(x + 1, B0, B1, A0, A1);
+    for (int i = 0; i < mm.n; i += 2) {
+        step(mm.xs + i * mm.dx, A0, A1, B0, B1);
+        if (i + 1 >= mm.n) break;
+        step(mm.xs + (i + 1) * mm.dx, B0, B1, A0, A1);
     }
-    slab_end(a, sl);
     step_end<T, 1>(a, sc, s, 0.0);
 }
 

@@ -220,6 +220,9 @@ class SlabSession:
         self.plan = plan = SlabPlan(shape[0], self.world, self.rank, halo)
         local_shape = (plan.local_planes,) + tuple(shape[1:])
         p = nat.make_params(model, dtype_code(precision), local_shape, h, dt, **scalars)
+        # a stop criterion makes the library sum every chunk's volumes over the ranks on the device; without one the
+        # log holds the rank's own sums and `volumes()` reduces it once
+        self.has_stop = bool(np.isfinite(scalars.get("stopping_volume", np.inf)) or scalars.get("small_volume", 0.0) > 0)
         uploads = [(f, plan.extend(a)) for f, a in statics] + [(f, plan.extend(a)) for f, a in fields_in]
         self.fields = [f for f, _ in fields_in]
         self.stepper = CudaSlabStepper(plan, p, uploads, self.fields, device, ipc=(driver in ("p2p", "fused")))
@@ -302,7 +305,7 @@ class SlabSession:
         torch = self.torch
         st = self.sync()
         vols = self.sim.volumes(0, st.steps_run)
-        if self.world > 1 and self.driver != "fused":      # the fused driver logs globally reduced volumes already
+        if self.world > 1 and not (self.driver == "fused" and self.has_stop):
             v = torch.from_numpy(vols).to(f"cuda:{self.device}")
             self.dist.all_reduce(v)
             vols = v.cpu().numpy()
@@ -395,6 +398,17 @@ def session_dti(u0, rgb, Dw, rho, dt, dx, dy, dz, halo=1, precision="fp64", devi
     """A reusable decomposed FK_DTI problem (bench.py: reset / run / sync_ms repeatedly)."""
     model, fields, statics, scalars = _dti_args(u0, rgb, Dw, rho, np.inf, 0.0)
     return SlabSession(model, fields, statics, scalars, np.shape(u0), (dx, dy, dz), dt, halo, precision, device, ("u",), driver)
+
+
+def session_fk2c(P0, N0, S0, WM, GM, th, th_necro, Dw, ratio, Ds, rho, lambda_np, sigma_np, lambda_s, dt, dx, dy, dz,
+                 halo=1, precision="fp64", device=0, driver="fused"):
+    """A reusable decomposed FK_2c problem (bench.py)."""
+    from . import _native as nat
+    return SlabSession(nat.MODEL_FK_2C, [(nat.FIELD_P, P0), (nat.FIELD_N, N0), (nat.FIELD_S, S0)],
+                       [(nat.FIELD_WM, WM), (nat.FIELD_GM, GM)],
+                       _scalars(rho=rho, Dw=Dw, ratio=ratio, th_matter=th, th_necro=th_necro, Ds=Ds, lambda_np=lambda_np,
+                                sigma_np=sigma_np, lambda_s=lambda_s), np.shape(P0), (dx, dy, dz), dt, halo, precision, device,
+                       ("P", "N", "S"), driver)
 
 
 def fk2c_loop(P0, N0, S0, WM, GM, th, th_necro, Dw, ratio, Ds, rho, lambda_np, sigma_np, lambda_s, dt, dx, dy, dz,
