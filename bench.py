@@ -398,7 +398,7 @@ def workload_config(pb, precision, gpus, slab=None):
 
 
 # ------------------------------------------------------------------------------------------
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     """Reference arm: rank 0 alone, every host core the process may use."""
     if rank != 0:
         return
@@ -434,7 +434,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "GLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -598,8 +598,18 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    # the contract is ONE JSON line on stdout: libraries that print there (NCCL announces its version when a communicator
+    # is created) are sent to stderr for the whole run, the line is written to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(line):
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
+
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
 
     import torch
@@ -655,7 +665,7 @@ def main():
                 "note": "N = 1 of this bench is BASELINE.json configs[1] (FK_2c, one GPU); N > 1 is configs[4] (this line) + configs[3] "
                         "(`ensemble`): compare N > 1 values with slab.one_gpu_glups, not with the N = 1 line",
             }
-            print(json.dumps(line))
+            emit(line)
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()
@@ -763,7 +773,7 @@ def main():
     del flush
     if args.patients > 0 and args.model == "fk2c":
         line["ensemble"] = ensemble_leg(args, rank, world, device, None)
-    print(json.dumps(line))
+    emit(line)
 
 
 if __name__ == "__main__":

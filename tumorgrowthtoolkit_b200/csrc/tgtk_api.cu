@@ -17,6 +17,7 @@
 #include "tgtk_kernels_v3.cuh"
 #include "tgtk_kernels_v5.cuh"
 #include "tgtk_kernels_tb.cuh"
+#include "tgtk_kernels_tma.cuh"
 #include "tgtk_elongate.cuh"
 
 using namespace tgtk;
@@ -120,6 +121,10 @@ struct tgtk_sim {
     dim3 tb_grid, tb_block;
     int tb_lx = 0;
     unsigned tb_nblocks = 0, ring_stride = 0, chunk_tb_mask = 0;
+    // variant 7 (tgtk_kernels_tma.cuh): tensor maps of the five arrays an FK_2c launch reads, per ping-pong parity
+    TmaSet tma[2];
+    bool tma_ready = false;
+    int tma_rows = 4, tma_stages = 3, tma_minb = 3;   // thread rows of the consumer tile (4: 32x8 voxels, 8: 32x16), pipeline depth
     std::vector<void *> snaps;     // one allocation per snapshot: nfields * n * elem
     std::vector<int> snap_steps;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -366,6 +371,12 @@ static bool has_v5(const tgtk_sim *s)
     return s->p.dtype == TGTK_F32 && (m == TGTK_MODEL_FK || m == TGTK_MODEL_FK_2C || m == TGTK_MODEL_DTI);
 }
 
+// 7 = FK_2c with TMA tile staging and a producer warp (tgtk_kernels_tma.cuh); needs 16-byte global strides
+static bool tma_ok(const tgtk_sim *s)
+{
+    return s->p.model == TGTK_MODEL_FK_2C && ((s->sy * s->elem) % 16) == 0 && (uint64_t)s->p.X * (uint64_t)s->sx < (1ull << 31);
+}
+
 // 5 / 6 = the fp32 z-pair kernels with four / two voxels per thread (tgtk_kernels_v5.cuh); fp64 has no
 // such family and runs the two-voxel kernels (4) instead.  Auto (0): measured on B200 the
 // z-pair kernels win for FK_DTI (four arrays streamed per voxel, one through shared memory: 64-bit
@@ -375,6 +386,7 @@ static int effective_variant(const tgtk_sim *s)
 {
     if (s->slab_on) return 4;              // the in-kernel halo push lives in the two-voxel kernels
     if (s->variant == 0) return (has_v5(s) && s->p.model == TGTK_MODEL_DTI) ? 6 : 4;
+    if (s->variant == 7) return tma_ok(s) ? 7 : 4;
     if (s->variant >= 5) return has_v5(s) ? s->variant : 4;
     return s->variant;
 }
@@ -415,10 +427,105 @@ template <typename... KA, typename... A> static cudaError_t launch_v4(tgtk_sim *
     return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
+// ---- variant 7: tensor maps and launch -------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {   // the driver entry point through the runtime: the library does not link libcuda
+        void *q = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &st) == cudaSuccess && st == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)q;
+    }
+    return fn;
+}
+
+// (X, Y, Z) array with pitches (sx, sy) as a rank-3 tensor {Z, Y, X}; box = {bz, by, 1} elements; outside -> zeros
+static int make_map(tgtk_sim *s, CUtensorMap *m, void *base, int bz, int by)
+{
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return fail("cuTensorMapEncodeTiled", "driver entry point not available");
+    const cuuint64_t dims[3] = {(cuuint64_t)s->p.Z, (cuuint64_t)s->p.Y, (cuuint64_t)s->p.X};
+    const cuuint64_t strides[2] = {(cuuint64_t)s->sy * s->elem, (cuuint64_t)s->sx * s->elem};
+    const cuuint32_t box[3] = {(cuuint32_t)bz, (cuuint32_t)by, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = enc(m, s->elem == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           by > 1 && bz > 4 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled", "encoding failed");
+    return 0;
+}
+
+static int build_tma(tgtk_sim *s)
+{
+    const int tyv = 2 * s->tma_rows, cw = 16 / (int)s->elem, rs = 32 + cw;
+    for (int par = 0; par < 2; ++par) {
+        void *arr[5] = {s->state[par][0], s->state[par][1], s->state[par][2], s->coef[0], s->coef[1]};
+        for (int f = 0; f < 5; ++f) {
+            if (make_map(s, &s->tma[par].main[f], arr[f], rs, tyv + 2)) return 1;
+            if (make_map(s, &s->tma[par].col[f], arr[f], cw, tyv + 2)) return 1;
+            if (make_map(s, &s->tma[par].row[f], arr[f], rs, 1)) return 1;
+        }
+    }
+    s->tma_ready = true;
+    return 0;
+}
+
+template <typename T, int TYT, int NST, int MINB> static cudaError_t launch_tma_k(tgtk_sim *s, const StepArgs<T> &a)
+{
+    auto kern = fk2c_step_tma<T, TYT, NST, MINB>;
+    const int smem = TmaGeom<T, TYT>::smem_bytes(NST);
+    static bool attr_set = false;      // per instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = s->grid;
+    cfg.blockDim = s->block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (effective_pdl(s) && s->cur_slot > 0) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, a, s->lx, s->tma[s->cur_par]);
+}
+
+template <typename T> static cudaError_t launch_tma(tgtk_sim *s, const StepArgs<T> &a)
+{
+    if (!s->tma_ready && build_tma(s)) return cudaErrorInvalidValue;
+    if (s->tma_rows == 8) return (s->tma_stages == 2) ? launch_tma_k<T, 8, 2, 2>(s, a) : launch_tma_k<T, 8, 3, 2>(s, a);
+    if (s->tma_stages == 2) return launch_tma_k<T, 4, 2, 4>(s, a);
+    return (s->tma_minb >= 4) ? launch_tma_k<T, 4, 3, 4>(s, a) : launch_tma_k<T, 4, 3, 3>(s, a);
+}
+
+template <typename T> static const void *tma_kernel(const tgtk_sim *s, int *smem)
+{
+    if (s->tma_rows == 8) {
+        *smem = TmaGeom<T, 8>::smem_bytes(s->tma_stages == 2 ? 2 : 3);
+        return (s->tma_stages == 2) ? (const void *)fk2c_step_tma<T, 8, 2, 2> : (const void *)fk2c_step_tma<T, 8, 3, 2>;
+    }
+    *smem = TmaGeom<T, 4>::smem_bytes(s->tma_stages == 2 ? 2 : 3);
+    if (s->tma_stages == 2) return (const void *)fk2c_step_tma<T, 4, 2, 4>;
+    return (s->tma_minb >= 4) ? (const void *)fk2c_step_tma<T, 4, 3, 4> : (const void *)fk2c_step_tma<T, 4, 3, 3>;
+}
+
 template <typename T> static cudaError_t launch_step(tgtk_sim *s)
 {
     StepArgs<T> a;
     fill_args(s, a);
+    if (s->lx > 0 && effective_variant(s) == 7) {
+        if (s->sy != s->p.Z) s->pads_dirty = true;
+        return launch_tma<T>(s, a);
+    }
     if constexpr (sizeof(T) == 4) {
         if (s->lx > 0 && effective_variant(s) == 5) {   // fp32: four voxels per thread
             const int mb = s->minb ? s->minb : 4;
@@ -607,6 +714,29 @@ static int configure_launch(tgtk_sim *s)
     const bool fits32 = (uint64_t)p.X * (uint64_t)s->sx < (1ull << 31);   // 32-bit element offsets
     const int variant = effective_variant(s);
     const int NX = s->slab_on ? s->slab_owned : p.X;       // planes a launch computes
+    s->tma_ready = false;
+    if (variant == 7) {
+        // 32 x 2*rows voxel tile on 32 x rows consumer threads + one producer warp; x cut into segments for whole waves
+        const int rows = s->tma_rows, tyv = 2 * rows;
+        const int tiles = ((p.Z + 31) / 32) * ((p.Y + tyv - 1) / tyv);
+        int per_sm = 2, sms = 148, smem = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+        const void *fn = (p.dtype == TGTK_F64) ? tma_kernel<double>(s, &smem) : tma_kernel<float>(s, &smem);
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 32 * (rows + 1), smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        const double slots = (double)sms * per_sm;
+        int best_lx = NX;
+        double best_eff = -1.0;
+        for (int lx = 1; lx <= NX; ++lx) {
+            const int ns = (NX + lx - 1) / lx;
+            const double waves = tiles * (double)ns / slots;
+            const double eff = waves / std::ceil(waves) * (lx / (lx + 1.0)) * ((double)NX / ((double)ns * lx));   // two extra tile loads per segment
+            if (eff > best_eff + 1e-9) { best_eff = eff; best_lx = lx; }
+        }
+        s->lx = best_lx;
+        s->block = dim3(32, rows + 1, 1);
+        s->grid = dim3((p.Z + 31) / 32, (p.Y + tyv - 1) / tyv, (NX + best_lx - 1) / best_lx);
+    } else
     if (variant >= 2 && has_v2(p.model) && fits32) {
         int best_tz = 32;
         double best = 1e30;
@@ -1069,8 +1199,9 @@ int tgtk_sim_create_ex(tgtk_sim **out, const tgtk_params *params, int device, vo
     }
     s->n = (size_t)p.X * p.Y * p.Z;
     s->elem = (p.dtype == TGTK_F64) ? 8 : 4;
-    // fp32 rows have an even pitch: every (row, even z) pair is 8-byte aligned for the v5 kernels
-    s->sy = p.Z + ((p.dtype == TGTK_F32) ? (p.Z & 1) : 0);
+    // rows have an even pitch: every (row, even z) pair of fp32 is 8-byte aligned for the z-pair kernels, and every
+    // row of either type starts on a 16-byte boundary, which TMA tensor maps require of the global strides
+    s->sy = p.Z + (p.Z & 1);
     s->sx = (int64_t)p.Y * s->sy;
     s->nfields = (p.model == TGTK_MODEL_FK_2C || p.model == TGTK_MODEL_FK2C_COEF12) ? 3 : 1;
     switch (p.model) {
@@ -1093,6 +1224,9 @@ int tgtk_sim_create_ex(tgtk_sim **out, const tgtk_params *params, int device, vo
     if (const char *v = getenv("TGTK_PDL")) s->pdl = atoi(v);
     if (const char *v = getenv("TGTK_TB")) s->tb = atoi(v);
     if (const char *v = getenv("TGTK_TB_ROWS")) s->tb_rows = atoi(v);
+    if (const char *v = getenv("TGTK_TMA_ROWS")) s->tma_rows = (atoi(v) == 8) ? 8 : 4;
+    if (const char *v = getenv("TGTK_TMA_STAGES")) s->tma_stages = (atoi(v) == 2) ? 2 : (atoi(v) == 4) ? 4 : 3;
+    if (const char *v = getenv("TGTK_TMA_MINB")) s->tma_minb = atoi(v);
     if (cudaDeviceGetAttribute(&s->l2_bytes, cudaDevAttrL2CacheSize, s->device) != cudaSuccess) s->l2_bytes = 0;
     *out = s;  // from here on tgtk_sim_destroy cleans up on failure
     if (configure_launch(s)) return 1;
@@ -1161,7 +1295,7 @@ void tgtk_sim_destroy(tgtk_sim *s)
 int tgtk_sim_set_variant(tgtk_sim *s, int variant)
 {
     if (!s) return fail("tgtk_sim_set_variant", "null argument");
-    if (variant < 0 || variant > 6) return fail("tgtk_sim_set_variant", "variant must be 0 (auto) or 1..6");
+    if (variant < 0 || variant > 7) return fail("tgtk_sim_set_variant", "variant must be 0 (auto) or 1..7");
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(s->stream));
     s->variant = variant;

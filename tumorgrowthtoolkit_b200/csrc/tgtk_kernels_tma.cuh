@@ -112,26 +112,30 @@ __global__ void __launch_bounds__(32 * (TYT + 1), MINB)
 
     double sP = 0.0, sN = 0.0;
     if (producer) {
-        // ---- producer warp: lanes 0..4 each feed one array ----------------------------------------------------
-        const int f = tz;
+        // ---- producer warp: one lane drives the TMA unit (UTMALDG takes uniform operands) --------------------------
         const uint32_t tx = 5u * (uint32_t)(G::MAIN_TX + ((zlo ? 1 : 0) + (zhi ? 1 : 0)) * G::COL_TX + ((ylo ? 1 : 0) + (yhi ? 1 : 0)) * G::ROW_TX);
         const L2Strip pf = l2_strip_setup(a, TYV);
         const bool pf_on = a.l2pf > 0 && blockIdx.x == 0 && tz == 5;  // a spare lane of the z = 0 tiles' producer
         const T *arrs[5] = {a.buf[sc.par][0], a.buf[sc.par][1], a.buf[sc.par][2], a.coef[0], a.coef[1]};
         int xp = (x0 == 0) ? a.X - 1 : x0 - 1;
+        int s = 0;
+        uint32_t ph = 0;                                             // parity of the phase load j completes on full[s]
         for (int j = 0; j < nload; ++j) {
-            const int s = j % NST;
-            if (j >= NST) mbar_wait(bar_empty + 8 * s, ((j / NST) & 1) ^ 1);
-            if (tz == 0) mbar_expect_tx(bar_full + 8 * s, tx);
-            __syncwarp();
-            if (f < 5) {
-                const uint32_t dst = stages_u32 + s * SS + f * FS, bar = bar_full + 8 * s;
-                tma_load_3d(dst, &maps.main[f], bar, z0 - 1, y0 - 1, xp);
-                if (zlo) tma_load_3d(dst + G::MAINB, &maps.col[f], bar, a.Z - G::CW, y0 - 1, xp);
-                if (zhi) tma_load_3d(dst + G::MAINB + G::COLB, &maps.col[f], bar, 0, y0 - 1, xp);
-                if (ylo) tma_load_3d(dst + G::MAINB + 2 * G::COLB, &maps.row[f], bar, z0 - 1, a.Y - 1, xp);
-                if (yhi) tma_load_3d(dst + G::MAINB + 2 * G::COLB + G::ROWB, &maps.row[f], bar, z0 - 1, 0, xp);
+            if (tz == 0) {
+                if (j >= NST) mbar_wait(bar_empty + 8 * s, ph ^ 1);  // the consumers are done with the previous tenant of the slot
+                const uint32_t bar = bar_full + 8 * s;
+                mbar_expect_tx(bar, tx);
+#pragma unroll
+                for (int f = 0; f < 5; ++f) {
+                    const uint32_t dst = stages_u32 + s * SS + f * FS;
+                    tma_load_3d(dst, &maps.main[f], bar, z0 - 1, y0 - 1, xp);
+                    if (zlo) tma_load_3d(dst + G::MAINB, &maps.col[f], bar, a.Z - G::CW, y0 - 1, xp);
+                    if (zhi) tma_load_3d(dst + G::MAINB + G::COLB, &maps.col[f], bar, 0, y0 - 1, xp);
+                    if (ylo) tma_load_3d(dst + G::MAINB + 2 * G::COLB, &maps.row[f], bar, z0 - 1, a.Y - 1, xp);
+                    if (yhi) tma_load_3d(dst + G::MAINB + 2 * G::COLB + G::ROWB, &maps.row[f], bar, z0 - 1, 0, xp);
+                }
             }
+            if (++s == NST) { s = 0; ph ^= 1; }
             if (pf_on) {                                             // the strip of the plane l2pf loads ahead into L2
                 const int xq = (xp + a.l2pf) % a.X;
                 const uint32_t q = (uint32_t)xq * pf.plane + pf.row0;
@@ -179,29 +183,35 @@ __global__ void __launch_bounds__(32 * (TYT + 1), MINB)
 
         Vox2c<T> A0, A1, B0, B1;
         T fp_lo0, fs_lo0, fp_lo1, fs_lo1;
-        int j = 0;                                                    // load index: plane x0-1 is load 0
+        // stage / phase parity of the load that holds the current plane (load 0 = plane x0-1, load 1 = plane x0, ...)
+        int sj = 0;
+        uint32_t phj = 0;
+        auto next_stage = [&](int &sn, uint32_t &phn) { sn = (sj + 1 == NST) ? 0 : sj + 1; phn = phj ^ (sn == 0 ? 1u : 0u); };
         {   // prologue: plane x0-1 only contributes the fluxes through the faces below plane x0
-            mbar_wait(bar_full + 8 * (j % NST), (j / NST) & 1);
-            const unsigned char *sb = stages + (j % NST) * SS;
+            mbar_wait(bar_full + 8 * sj, phj);
+            const unsigned char *sb = stages + sj * SS;
             Vox2c<T> M0, M1;
             own(M0, sb, o0); own(M1, sb, o1);
-            mbar_wait(bar_full + 8 * ((j + 1) % NST), ((j + 1) / NST) & 1);
-            const unsigned char *sa = stages + ((j + 1) % NST) * SS;
+            int sn; uint32_t phn;
+            next_stage(sn, phn);
+            mbar_wait(bar_full + 8 * sn, phn);
+            const unsigned char *sa = stages + sn * SS;
             own(A0, sa, o0); own(A1, sa, o1);
             fp_lo0 = relu(M0.k + A0.k) * (M0.p - A0.p);
             fs_lo0 = relu(M0.b + A0.b) * (M0.s - A0.s);
             fp_lo1 = relu(M1.k + A1.k) * (M1.p - A1.p);
             fs_lo1 = relu(M1.b + A1.b) * (M1.s - A1.s);
             __syncwarp();
-            if (lane0) mbar_arrive(bar_empty + 8 * (j % NST));
-            j = 1;
+            if (lane0) mbar_arrive(bar_empty + 8 * sj);
+            sj = sn; phj = phn;
         }
         auto step = [&](int x, const Vox2c<T> &c0, const Vox2c<T> &c1, Vox2c<T> &p0, Vox2c<T> &p1) {
-            // plane x is load j (already waited for), plane x+1 is load j+1
-            const unsigned char *sb = stages + (j % NST) * SS;
-            const int jn = j + 1;
-            mbar_wait(bar_full + 8 * (jn % NST), (jn / NST) & 1);
-            const unsigned char *sn = stages + (jn % NST) * SS;
+            // plane x sits in stage sj (already waited for), plane x+1 in the next one
+            const unsigned char *sb = stages + sj * SS;
+            int sn_; uint32_t phn;
+            next_stage(sn_, phn);
+            mbar_wait(bar_full + 8 * sn_, phn);
+            const unsigned char *sn = stages + sn_ * SS;
             own(p0, sn, o0); own(p1, sn, o1);
             // work that needs no neighbour
             const T H0 = heaviside50_fast(c0.s, a.sigma_np), H1 = heaviside50_fast(c1.s, a.sigma_np);
@@ -224,7 +234,7 @@ __global__ void __launch_bounds__(32 * (TYT + 1), MINB)
             ss1 += a.ez * (relu(at(fB, ol1) + c1.b) * (at(fS, ol1) - c1.s) - relu(c1.b + at(fB, or1)) * (c1.s - at(fS, or1)));
             // every read of plane x's stage is done: hand the slot back to the producer
             __syncwarp();
-            if (lane0) mbar_arrive(bar_empty + 8 * (j % NST));
+            if (lane0) mbar_arrive(bar_empty + 8 * sj);
             // x faces
             const T fp_hi0 = relu(c0.k + p0.k) * (c0.p - p0.p), fs_hi0 = relu(c0.b + p0.b) * (c0.s - p0.s);
             const T fp_hi1 = relu(c1.k + p1.k) * (c1.p - p1.p), fs_hi1 = relu(c1.b + p1.b) * (c1.s - p1.s);
@@ -246,7 +256,7 @@ __global__ void __launch_bounds__(32 * (TYT + 1), MINB)
             }
             fp_lo0 = fp_hi0; fs_lo0 = fs_hi0; fp_lo1 = fp_hi1; fs_lo1 = fs_hi1;
             g0 += gsx; g1 += gsx;
-            j = jn;
+            sj = sn_; phj = phn;
         };
         for (int x = x0; x < x1; x += 2) {
             step(x, A0, A1, B0, B1);
