@@ -359,7 +359,6 @@ template <typename T> static void fill_args(const tgtk_sim *s, StepArgs<T> &a)
         a.flags = s->slab_flags;
         a.flag_lo = s->peer_flags[0] + kSlabFromNext;     // I am the previous rank's "next"
         a.flag_hi = s->peer_flags[1] + kSlabFromPrev;
-        a.ntiles = s->grid.x * s->grid.y;
     }
 }
 
@@ -463,7 +462,7 @@ static int make_map(tgtk_sim *s, CUtensorMap *m, void *base, int bz, int by)
 
 static int build_tma(tgtk_sim *s)
 {
-    const int tyv = 2 * s->tma_rows, cw = 16 / (int)s->elem, rs = 32 + cw;
+    const int tyv = 2 * s->tma_rows, cw = 16 / (int)s->elem, rs = 32 + 2 * cw;      // TmaGeom::RS
     for (int par = 0; par < 2; ++par) {
         void *arr[5] = {s->state[par][0], s->state[par][1], s->state[par][2], s->coef[0], s->coef[1]};
         for (int f = 0; f < 5; ++f) {
@@ -777,9 +776,7 @@ static int configure_launch(tgtk_sim *s)
         const double slots = (double)sms * per_sm;
         int best_lx = NX;
         double best_eff = -1.0;
-        // fused slab mode: at least two segments, so that the lower one marches up and the upper one down and both
-        // boundary planes are pushed to the neighbours at the start of the step
-        const int lx_max = (s->slab_on && NX >= 2) ? (NX + 1) / 2 : NX;
+        const int lx_max = NX;
         for (int lx = 1; lx <= lx_max; ++lx) {
             const int ns = (NX + lx - 1) / lx;
             const double waves = tiles * (double)ns / slots;
@@ -969,7 +966,8 @@ static cudaError_t launch_chunk_finish(tgtk_sim *s, int count)
     if (e != cudaSuccess) return e;
     ++s->aux_launches;
     chunk_commit_kernel<<<1, 32, 0, s->stream>>>(s->ctrl, s->chunkvol, s->volumes, s->volumes_cap, count, spec, p.stopping_volume,
-                                               p.small_volume, s->slab_flags);
+                                               p.small_volume, s->slab_flags, s->peer_flags[0] + kSlabFromNext,
+                                               s->peer_flags[1] + kSlabFromPrev);
     return cudaGetLastError();
 }
 

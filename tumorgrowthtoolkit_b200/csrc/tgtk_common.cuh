@@ -61,20 +61,21 @@ template <typename T> struct StepArgs {
     int x_lo, x_hi;
     // Fused slab mode (tgtk_nccl.inc, one rank per GPU, axis 0 decomposed, one ghost plane per side): the blocks
     // that compute the rank's lowest / highest owned plane ALSO store it into the neighbouring rank's ghost plane
-    // (peer-mapped memory, NVLink) and the last such block of the launch publishes the launch's epoch in the
-    // neighbour's flag word; the blocks that READ a ghost plane first wait until the neighbour has published the
-    // previous epoch.  No exchange launches, no copies between steps; interior blocks never wait.
+    // (peer-mapped memory, NVLink).  A launch's stores are visible system-wide when the launch has completed, so
+    // the NEXT launch of the stream (step, checkpoint or chunk commit) publishes "epoch e-1 is complete" in both
+    // neighbours' flag words as its first action, and only the blocks that read a ghost plane -- scheduled last --
+    // wait for the neighbours' word.  No exchange launches, no copies, no fences inside the step; interior blocks
+    // never wait.
     int slab;                 // 0: off
     T *peer_lo[2][3];         // previous rank's state buffers [ping-pong][field]
     T *peer_hi[2][3];         // next rank's
     uint32_t off_lo, off_hi;  // added (mod 2^32) to an element offset in my plane x_lo / x_hi-1: the neighbour's ghost element
     int *flags;               // my words (SlabWord): written by the neighbours
     int *flag_lo, *flag_hi;   // the word this rank publishes in the previous / next rank's memory
-    unsigned ntiles;          // blocks per plane segment (gridDim.x * gridDim.y)
 };
 
 // words of the slab flag array (one cudaMalloc per rank, mapped by both neighbours)
-enum SlabWord { kSlabFromPrev = 8, kSlabFromNext = 9, kSlabEpoch = 10, kSlabTicketLo = 12, kSlabTicketHi = 13, kSlabError = 4 };
+enum SlabWord { kSlabFromPrev = 8, kSlabFromNext = 9, kSlabEpoch = 10, kSlabError = 4 };
 
 __device__ __forceinline__ int ld_acquire_sys(const int *p)
 {
@@ -103,6 +104,14 @@ __device__ __forceinline__ void slab_spin(int *flags, int w0, int w1, int epoch)
     }
 }
 
+// first action of every launch of a decomposed run: whatever the stream ran before this launch has completed, its
+// stores into the neighbours' ghost planes included -- say so
+__device__ __forceinline__ void slab_publish(int *flag_lo, int *flag_hi, int done_epoch)
+{
+    st_release_sys(flag_lo, done_epoch);
+    st_release_sys(flag_hi, done_epoch);
+}
+
 struct SlabCtl {
     bool lo, hi;   // this block computes the rank's lowest / highest owned plane (reads that ghost, pushes that plane)
     int epoch;     // of this launch
@@ -118,30 +127,13 @@ template <typename T> __device__ __forceinline__ SlabCtl slab_begin(const StepAr
     c.lo = (x0 == a.x_lo);
     c.hi = (x1 == a.x_hi);
     c.epoch = a.flags[kSlabEpoch] + a.slot + 1;      // only chunk_commit_kernel writes the base, never beside a step launch
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0 && threadIdx.y == 0)
+        slab_publish(a.flag_lo, a.flag_hi, c.epoch - 1);
     if (c.lo || c.hi) {
         if (threadIdx.x == 0 && threadIdx.y == 0) slab_spin(a.flags, c.lo ? kSlabFromPrev : -1, c.hi ? kSlabFromNext : -1, c.epoch - 1);
         __syncthreads();
     }
     return c;
-}
-
-// right after a block has stored a boundary plane into the neighbour's ghost plane (side 0: lowest owned plane ->
-// previous rank, 1: highest -> next rank): the stores are made visible system-wide and the LAST block of that side
-// publishes the launch's epoch in the neighbour's flag word.  By then every block of the side has also consumed its
-// own ghost plane of the buffer this launch reads (its result depends on it), so the neighbour may overwrite it.
-// Block-uniform; contains a __syncthreads().
-template <typename T> __device__ __forceinline__ void slab_signal(const StepArgs<T> &a, const SlabCtl &c, int side)
-{
-    __syncthreads();
-    if (threadIdx.x == 0 && threadIdx.y == 0) {
-        __threadfence_system();
-        int *ticket = a.flags + (side ? kSlabTicketHi : kSlabTicketLo);
-        if (atomicAdd((unsigned *)ticket, 1u) == a.ntiles - 1) {
-            *ticket = 0;
-            __threadfence_system();
-            st_release_sys(side ? a.flag_hi : a.flag_lo, c.epoch);
-        }
-    }
 }
 
 // L2 prefetch of the rows [y0, y0+rows) of plane xp of one array: rows of a plane are contiguous
@@ -450,10 +442,11 @@ __global__ void __launch_bounds__(256) chunk_finish_kernel(Ctrl *ctrl, const dou
 
 // fused slab mode: the second half of chunk_finish_kernel, after the chunk's volumes have been all-reduced
 __global__ void chunk_commit_kernel(Ctrl *ctrl, const double *chunkvol, double *volumes, int volumes_cap, int count, int spec,
-                                    double stop_volume, double small_volume, int *flags)
+                                    double stop_volume, double small_volume, int *flags, int *flag_lo, int *flag_hi)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (spec && ctrl->stop_reason != 0) return;       // a voided chunk: its launches published nothing, the epoch stays
+    if (spec && ctrl->stop_reason != 0) return;       // a voided chunk: its launches did nothing, the epoch stays
+    slab_publish(flag_lo, flag_hi, flags[kSlabEpoch] + count);      // the chunk's last step launch has completed
     const int t0 = ctrl->t;
     int trip = -1, reason = 0;
     double v = 0.0;
@@ -480,8 +473,9 @@ __global__ void chunk_commit_kernel(Ctrl *ctrl, const double *chunkvol, double *
 }
 
 // speculative mode: the state before a chunk, kept until the chunk's stop tests have passed
-// (flags != nullptr, fused slab mode: the ghost planes are part of that state -- wait until both neighbours'
-// pushes of the previous launch have landed)
+// (flags != nullptr, fused slab mode: the ghost planes are part of that state -- wait until both neighbours have
+// said that every launch up to the current epoch, and with it every store into this rank's ghost planes, is complete;
+// chunk_commit_kernel, which precedes this launch in the stream, said the same for this rank)
 __global__ void __launch_bounds__(256) checkpoint_kernel(const Ctrl *ctrl, const uint2 *s0, const uint2 *s1, const uint2 *s2,
                                                          uint2 *d0, uint2 *d1, uint2 *d2, size_t n8, int *flags)
 {

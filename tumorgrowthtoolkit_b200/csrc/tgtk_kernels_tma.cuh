@@ -15,7 +15,9 @@
 // The arithmetic is fk2c_step_v4's, expression by expression (bitwise equal results).
 //
 // Requirements (checked by the host, which otherwise keeps variant 4): even row pitch (16-byte global strides),
-// Z >= 16 / sizeof(T), 32-bit element offsets.
+// 32-bit element offsets.  Measured on B200 (tools/probes/tma_probe.cu): the innermost START COORDINATE of a box must
+// be a multiple of 16 bytes too -- an odd z start for fp64 raises "illegal instruction" -- negative and out-of-range
+// aligned starts are fine (zero fill).  Hence the tile starts CW = 16 / sizeof(T) elements left of z0, not one.
 #pragma once
 #include <cuda.h>
 #include "tgtk_common.cuh"
@@ -63,7 +65,7 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
 template <typename T, int TYT> struct TmaGeom {
     static constexpr int TZ = 32, TYV = 2 * TYT;
     static constexpr int CW = 16 / (int)sizeof(T);                  // elements of a 16-byte column strip
-    static constexpr int RS = TZ + CW;                              // tile row in elements: z0-1 .. z0+TZ (+ unused tail in fp32)
+    static constexpr int RS = TZ + 2 * CW;                          // tile row in elements: z0-CW .. z0+TZ+CW-1 (16-byte aligned start)
     static constexpr int MAINB = ((RS * (TYV + 2) * (int)sizeof(T) + 127) / 128) * 128;
     static constexpr int COLB = ((16 * (TYV + 2) + 127) / 128) * 128;
     static constexpr int ROWB = ((RS * (int)sizeof(T) + 127) / 128) * 128;
@@ -98,6 +100,7 @@ __global__ void __launch_bounds__(32 * (TYT + 1), MINB)
     const int nload = x1 - x0 + 2;                                   // planes x0-1 .. x1, in march order
     // block-uniform: which box faces this tile touches
     const bool zlo = (z0 == 0), zhi = (z0 + TZ >= a.Z), ylo = (y0 == 0), yhi = (y0 + TYV >= a.Y);
+    const int zlast = ((a.Z - 1) / G::CW) * G::CW;                   // aligned start of the column strip that holds z = Z-1
 
     if (tz == 0 && ty == 0) {
         for (int s = 0; s < NST; ++s) {
@@ -128,11 +131,11 @@ __global__ void __launch_bounds__(32 * (TYT + 1), MINB)
 #pragma unroll
                 for (int f = 0; f < 5; ++f) {
                     const uint32_t dst = stages_u32 + s * SS + f * FS;
-                    tma_load_3d(dst, &maps.main[f], bar, z0 - 1, y0 - 1, xp);
-                    if (zlo) tma_load_3d(dst + G::MAINB, &maps.col[f], bar, a.Z - G::CW, y0 - 1, xp);
+                    tma_load_3d(dst, &maps.main[f], bar, z0 - G::CW, y0 - 1, xp);
+                    if (zlo) tma_load_3d(dst + G::MAINB, &maps.col[f], bar, zlast, y0 - 1, xp);
                     if (zhi) tma_load_3d(dst + G::MAINB + G::COLB, &maps.col[f], bar, 0, y0 - 1, xp);
-                    if (ylo) tma_load_3d(dst + G::MAINB + 2 * G::COLB, &maps.row[f], bar, z0 - 1, a.Y - 1, xp);
-                    if (yhi) tma_load_3d(dst + G::MAINB + 2 * G::COLB + G::ROWB, &maps.row[f], bar, z0 - 1, 0, xp);
+                    if (ylo) tma_load_3d(dst + G::MAINB + 2 * G::COLB, &maps.row[f], bar, z0 - G::CW, a.Y - 1, xp);
+                    if (yhi) tma_load_3d(dst + G::MAINB + 2 * G::COLB + G::ROWB, &maps.row[f], bar, z0 - G::CW, 0, xp);
                 }
             }
             if (++s == NST) { s = 0; ph ^= 1; }
@@ -154,15 +157,16 @@ __global__ void __launch_bounds__(32 * (TYT + 1), MINB)
         // byte offsets inside one array's region of a stage; fixed for the whole march
         constexpr int col_lo = G::MAINB, col_hi = G::MAINB + G::COLB;
         constexpr int row_lo = G::MAINB + 2 * G::COLB, row_hi = row_lo + G::ROWB;
-        const int t0 = ((2 * ty + 1) * RS + tz + 1) * ES;             // tile slot of (r0, z)
+        const int t0 = ((2 * ty + 1) * RS + tz + G::CW) * ES;         // tile slot of (r0, z)
         int o0 = t0, o1 = t0 + RS * ES, oup = t0 - RS * ES, odn = t0 + 2 * RS * ES;
         int ol0 = o0 - ES, or0 = o0 + ES, ol1 = o1 - ES, or1 = o1 + ES;
-        if (r0 == 0) oup = row_lo + (tz + 1) * ES;                    // y = -1 -> Y-1
-        if (r0 + 1 == a.Y) o1 = ol1 = or1 = odn = row_hi + (tz + 1) * ES;   // the lower own row is y = Y -> 0 (shadow, nothing stored)
-        else if (r0 + 2 == a.Y) odn = row_hi + (tz + 1) * ES;        // y = Y -> 0
-        if (z == 0) {                                                 // z = -1 -> Z-1: last element of the strip that starts at Z - CW
-            ol0 = col_lo + ((2 * ty + 1) * G::CW + G::CW - 1) * ES;
-            if (r0 + 1 != a.Y) ol1 = col_lo + ((2 * ty + 2) * G::CW + G::CW - 1) * ES;
+        if (r0 == 0) oup = row_lo + (tz + G::CW) * ES;                // y = -1 -> Y-1
+        if (r0 + 1 == a.Y) o1 = ol1 = or1 = odn = row_hi + (tz + G::CW) * ES;   // the lower own row is y = Y -> 0 (shadow, nothing stored)
+        else if (r0 + 2 == a.Y) odn = row_hi + (tz + G::CW) * ES;    // y = Y -> 0
+        if (z == 0) {                                                 // z = -1 -> Z-1, inside the strip that starts at zlast
+            const int e = a.Z - 1 - zlast;
+            ol0 = col_lo + ((2 * ty + 1) * G::CW + e) * ES;
+            if (r0 + 1 != a.Y) ol1 = col_lo + ((2 * ty + 2) * G::CW + e) * ES;
         }
         if (z + 1 == a.Z) {                                           // z = Z -> 0: first element of the strip that starts at 0
             or0 = col_hi + ((2 * ty + 1) * G::CW) * ES;

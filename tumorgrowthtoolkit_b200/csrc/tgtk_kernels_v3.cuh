@@ -295,7 +295,11 @@ __device__ __forceinline__ Stage2 stage2_setup(const StepArgs<T> &a, int lx)
     const int r0 = y0 + 2 * ty;
     g.valid0 = (z0 + tz < a.Z) && (r0 < a.Y);
     g.valid1 = (z0 + tz < a.Z) && (r0 + 1 < a.Y);
-    g.x0 = a.x_lo + blockIdx.z * lx;
+    // fused slab mode: the two segments that read a ghost plane get the highest block indices -- they are scheduled
+    // last, when the neighbours' words have long arrived
+    int seg = blockIdx.z;
+    if (a.slab && gridDim.z > 2) seg = (seg + 2 < (int)gridDim.z) ? seg + 1 : (seg + 2 == (int)gridDim.z ? 0 : seg);
+    g.x0 = a.x_lo + seg * lx;
     g.x1 = min(g.x0 + lx, a.x_hi);
     g.sx = (uint32_t)a.sx;
     g.wrap_back = (uint32_t)(a.X - 1) * g.sx;
@@ -317,10 +321,10 @@ __device__ __forceinline__ Stage2 stage2_setup(const StepArgs<T> &a, int lx)
     return g;
 }
 
-// Marching direction of a block.  Fused slab mode: the segments of the upper half of the rank's planes march
-// DOWNWARDS, so that both boundary planes of the rank are computed -- and pushed to the neighbours -- at the very
-// start of the step and their epochs arrive long before the neighbours' next step needs them.  The face fluxes are
-// antisymmetric and the sums commutative, so a voxel's result does not depend on the direction (bitwise).
+// Marching direction of a block: up (x0 -> x1-1) or down.  The face fluxes are antisymmetric and the sums
+// commutative, so a voxel's result does not depend on the direction (bitwise).  Downward marching is not used at
+// present: it was written to get a slab's upper boundary plane out early, which the kernel-boundary publication
+// of the fused slab driver made unnecessary.
 struct March2 {
     bool down;
     int xs, dx, n;            // first plane, +-1, number of planes
@@ -332,7 +336,7 @@ struct March2 {
 template <typename T> __device__ __forceinline__ March2 march2_setup(const StepArgs<T> &a, Stage2 &g)
 {
     March2 m;
-    m.down = a.slab && gridDim.z > 1 && 2 * blockIdx.z >= gridDim.z;
+    m.down = false;           // (kept for experiments: with kernel-boundary publication the push time inside a step is irrelevant)
     m.n = g.x1 - g.x0;
     m.xs = g.x0;
     m.dx = 1;
@@ -464,8 +468,8 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> 
             Po[g.c1] = pn1; No[g.c1] = nn1; So[g.c1] = sn1;
             if (cnt) { sP += (double)pn1; sN += (double)nn1; }
         }
-        if (sl.lo && x == a.x_lo) { push(a.peer_lo[sc.par ^ 1], a.off_lo, pn0, nn0, sn0, pn1, nn1, sn1); slab_signal(a, sl, 0); }
-        if (sl.hi && x == a.x_hi - 1) { push(a.peer_hi[sc.par ^ 1], a.off_hi, pn0, nn0, sn0, pn1, nn1, sn1); slab_signal(a, sl, 1); }
+        if (sl.lo && x == a.x_lo) { push(a.peer_lo[sc.par ^ 1], a.off_lo, pn0, nn0, sn0, pn1, nn1, sn1); }
+        if (sl.hi && x == a.x_hi - 1) { push(a.peer_hi[sc.par ^ 1], a.off_hi, pn0, nn0, sn0, pn1, nn1, sn1); }
         fp_lo0 = fp_hi0; fs_lo0 = fs_hi0; fp_lo1 = fp_hi1; fs_lo1 = fs_hi1;
         g.c0 = n0; g.c1 = n1;
         buf ^= 1;
@@ -544,8 +548,8 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk_step_v4(const StepArgs<T> a,
         const bool cnt = counts(a, x);
         if (g.valid0) { out[g.c0] = un0; if (cnt) s += (double)un0; }
         if (g.valid1) { out[g.c1] = un1; if (cnt) s += (double)un1; }
-        if (sl.lo && x == a.x_lo) { push(a.peer_lo[sc.par ^ 1], a.off_lo, un0, un1); slab_signal(a, sl, 0); }
-        if (sl.hi && x == a.x_hi - 1) { push(a.peer_hi[sc.par ^ 1], a.off_hi, un0, un1); slab_signal(a, sl, 1); }
+        if (sl.lo && x == a.x_lo) { push(a.peer_lo[sc.par ^ 1], a.off_lo, un0, un1); }
+        if (sl.hi && x == a.x_hi - 1) { push(a.peer_hi[sc.par ^ 1], a.off_hi, un0, un1); }
         f_lo0 = f_hi0; f_lo1 = f_hi1;
         g.c0 = n0; g.c1 = n1;
         buf ^= 1;
@@ -627,8 +631,8 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) dti_step_v4(const StepArgs<T> a
         const bool cnt = counts(a, x);
         if (g.valid0) { out[g.c0] = un0; if (cnt) s += (double)un0; }
         if (g.valid1) { out[g.c1] = un1; if (cnt) s += (double)un1; }
-        if (sl.lo && x == a.x_lo) { push(a.peer_lo[sc.par ^ 1], a.off_lo, un0, un1); slab_signal(a, sl, 0); }
-        if (sl.hi && x == a.x_hi - 1) { push(a.peer_hi[sc.par ^ 1], a.off_hi, un0, un1); slab_signal(a, sl, 1); }
+        if (sl.lo && x == a.x_lo) { push(a.peer_lo[sc.par ^ 1], a.off_lo, un0, un1); }
+        if (sl.hi && x == a.x_hi - 1) { push(a.peer_hi[sc.par ^ 1], a.off_hi, un0, un1); }
         um0 = c0.u; um1 = c1.u;
         g.c0 = n0; g.c1 = n1;
         buf ^= 1;
