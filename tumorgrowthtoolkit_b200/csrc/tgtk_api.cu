@@ -323,6 +323,9 @@ template <typename T> static void fill_args(const tgtk_sim *s, StepArgs<T> &a)
         a.ey = (T)(2.0 / (4.0 * p.h[0] * p.h[2]));
         a.ez = (T)(2.0 / (4.0 * p.h[1] * p.h[2]));
     }
+    const T half = (T)Relu2<T>::scale;
+    a.hx = half * a.cx; a.hy = half * a.cy; a.hz = half * a.cz;
+    a.gx = half * a.ex; a.gy = half * a.ey; a.gz = half * a.ez;
     a.dt = (T)p.dt; a.rho = (T)p.rho;
     a.th_necro = (T)p.th_necro; a.lambda_np = (T)p.lambda_np; a.sigma_np = (T)p.sigma_np; a.lambda_s = (T)p.lambda_s;
     a.vol_scale_p = p.h[0] * p.h[1] * p.h[2];

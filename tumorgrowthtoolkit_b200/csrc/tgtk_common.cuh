@@ -31,6 +31,9 @@ template <typename T> struct StepArgs {
     const T *coef[12];     // model dependent, see tgtk_api.cu
     T cx, cy, cz;          // FK/FK_2c: Dw/h^2 ; DTI/COEF6/FACES: 1/h^2
     T ex, ey, ez;          // FK_2c: Ds/h^2
+    T hx, hy, hz, gx, gy, gz;   // the same six constants for the two-voxel kernels, which take max(x, 0) as relu2(x) = x + |x| = 2 max(x, 0)
+                                // in fp64 (ONE fp64-pipe instruction, |x| is an operand modifier, instead of a compare and two selects): the
+                                // constants carry the factor 1/2 -- exact, a power of two -- so every product is bit for bit the same
     T dt, rho;
     T th_necro, lambda_np, sigma_np, lambda_s;
     double vol_scale_p;    // dx*dy*dz
@@ -242,6 +245,17 @@ __device__ __forceinline__ double relu(double x)
     return __hiloint2double(hi & keep, __double2loint(x) & keep);
 }
 __device__ __forceinline__ float relu(float x) { return fmaxf(x, 0.0f); }
+
+// 2 max(x, 0) for the two-voxel kernels (see StepArgs::hx): fp64 x + |x|, fp32 2 fmaxf (one FMNMX + the factor in the constant)
+#ifndef TGTK_NO_RELU2
+template <typename T> struct Relu2 { static constexpr double scale = 0.5; };
+__device__ __forceinline__ double relu2(double x) { return x + fabs(x); }
+__device__ __forceinline__ float relu2(float x) { return x + fabsf(x); }
+#else
+template <typename T> struct Relu2 { static constexpr double scale = 1.0; };
+__device__ __forceinline__ double relu2(double x) { return relu(x); }
+__device__ __forceinline__ float relu2(float x) { return relu(x); }
+#endif
 
 // smooth_heaviside, FK_2c/FK_2c.py:75-76 (k = 50)
 template <typename T> __device__ __forceinline__ T heaviside50(T s, T sigma)

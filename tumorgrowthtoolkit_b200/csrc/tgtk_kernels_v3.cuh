@@ -393,10 +393,10 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> 
     T fp_lo0, fs_lo0, fp_lo1, fs_lo1;      // fluxes through the faces below (x-1 | x)
     {
         const T pm0 = P[g.prev0], pm1 = P[g.prev1];
-        fp_lo0 = relu(keff(pm0, N[g.prev0], kc[g.prev0]) + A0.k) * (pm0 - A0.p);
-        fs_lo0 = relu(bc[g.prev0] + A0.b) * (S[g.prev0] - A0.s);
-        fp_lo1 = relu(keff(pm1, N[g.prev1], kc[g.prev1]) + A1.k) * (pm1 - A1.p);
-        fs_lo1 = relu(bc[g.prev1] + A1.b) * (S[g.prev1] - A1.s);
+        fp_lo0 = relu2(keff(pm0, N[g.prev0], kc[g.prev0]) + A0.k) * (pm0 - A0.p);
+        fs_lo0 = relu2(bc[g.prev0] + A0.b) * (S[g.prev0] - A0.s);
+        fp_lo1 = relu2(keff(pm1, N[g.prev1], kc[g.prev1]) + A1.k) * (pm1 - A1.p);
+        fs_lo1 = relu2(bc[g.prev1] + A1.b) * (S[g.prev1] - A1.s);
     }
     T hp = 0, hn = 0, hk = 0, hsv = 0, hb = 0;
     if (g.ring) { hp = P[g.h]; hn = N[g.h]; hk = kc[g.h]; hsv = S[g.h]; hb = bc[g.h]; }
@@ -432,30 +432,30 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> 
         const T react0 = a.rho * (c0.s * c0.p) * ((T(1) - c0.p) - c0.n) - (a.lambda_np * c0.p) * H0;
         const T react1 = a.rho * (c1.s * c1.p) * ((T(1) - c1.p) - c1.n) - (a.lambda_np * c1.p) * H1;
         // the face between the two own rows: no shared memory involved
-        const T fp_mid = relu(c0.k + c1.k) * (c0.p - c1.p);
-        const T fs_mid = relu(c0.b + c1.b) * (c0.s - c1.s);
+        const T fp_mid = relu2(c0.k + c1.k) * (c0.p - c1.p);
+        const T fs_mid = relu2(c0.b + c1.b) * (c0.s - c1.s);
         __syncthreads();
         const Pair<T> pu = tl[0][o0 - RS], pd = tl[0][o1 + RS];                       // rows y-1 and y+2: (P, k)
         const Pair<T> su = tl[1][o0 - RS], sd = tl[1][o1 + RS];                       // (S, b)
         const Pair<T> pl0 = tl[0][o0 - 1], pr0 = tl[0][o0 + 1], pl1 = tl[0][o1 - 1], pr1 = tl[0][o1 + 1];
         const Pair<T> sl0 = tl[1][o0 - 1], sr0 = tl[1][o0 + 1], sl1 = tl[1][o1 - 1], sr1 = tl[1][o1 + 1];
-        T sp0 = a.cy * (relu(pu.b + c0.k) * (pu.a - c0.p) - fp_mid);
-        T sp1 = a.cy * (fp_mid - relu(c1.k + pd.b) * (c1.p - pd.a));
-        T ss0 = a.ey * (relu(su.b + c0.b) * (su.a - c0.s) - fs_mid);
-        T ss1 = a.ey * (fs_mid - relu(c1.b + sd.b) * (c1.s - sd.a));
-        sp0 += a.cz * (relu(pl0.b + c0.k) * (pl0.a - c0.p) - relu(c0.k + pr0.b) * (c0.p - pr0.a));
-        sp1 += a.cz * (relu(pl1.b + c1.k) * (pl1.a - c1.p) - relu(c1.k + pr1.b) * (c1.p - pr1.a));
-        ss0 += a.ez * (relu(sl0.b + c0.b) * (sl0.a - c0.s) - relu(c0.b + sr0.b) * (c0.s - sr0.a));
-        ss1 += a.ez * (relu(sl1.b + c1.b) * (sl1.a - c1.s) - relu(c1.b + sr1.b) * (c1.s - sr1.a));
+        T sp0 = a.hy * (relu2(pu.b + c0.k) * (pu.a - c0.p) - fp_mid);
+        T sp1 = a.hy * (fp_mid - relu2(c1.k + pd.b) * (c1.p - pd.a));
+        T ss0 = a.gy * (relu2(su.b + c0.b) * (su.a - c0.s) - fs_mid);
+        T ss1 = a.gy * (fs_mid - relu2(c1.b + sd.b) * (c1.s - sd.a));
+        sp0 += a.hz * (relu2(pl0.b + c0.k) * (pl0.a - c0.p) - relu2(c0.k + pr0.b) * (c0.p - pr0.a));
+        sp1 += a.hz * (relu2(pl1.b + c1.k) * (pl1.a - c1.p) - relu2(c1.k + pr1.b) * (c1.p - pr1.a));
+        ss0 += a.gz * (relu2(sl0.b + c0.b) * (sl0.a - c0.s) - relu2(c0.b + sr0.b) * (c0.s - sr0.a));
+        ss1 += a.gz * (relu2(sl1.b + c1.b) * (sl1.a - c1.s) - relu2(c1.b + sr1.b) * (c1.s - sr1.a));
         // x faces last: plane x+1 has had the whole step to arrive
         p0.k = keff(p0.p, p0.n, p0.k);
         p1.k = keff(p1.p, p1.n, p1.k);
-        const T fp_hi0 = relu(c0.k + p0.k) * (c0.p - p0.p), fs_hi0 = relu(c0.b + p0.b) * (c0.s - p0.s);
-        const T fp_hi1 = relu(c1.k + p1.k) * (c1.p - p1.p), fs_hi1 = relu(c1.b + p1.b) * (c1.s - p1.s);
-        sp0 += a.cx * (fp_lo0 - fp_hi0);
-        sp1 += a.cx * (fp_lo1 - fp_hi1);
-        ss0 += a.ex * (fs_lo0 - fs_hi0);
-        ss1 += a.ex * (fs_lo1 - fs_hi1);
+        const T fp_hi0 = relu2(c0.k + p0.k) * (c0.p - p0.p), fs_hi0 = relu2(c0.b + p0.b) * (c0.s - p0.s);
+        const T fp_hi1 = relu2(c1.k + p1.k) * (c1.p - p1.p), fs_hi1 = relu2(c1.b + p1.b) * (c1.s - p1.s);
+        sp0 += a.hx * (fp_lo0 - fp_hi0);
+        sp1 += a.hx * (fp_lo1 - fp_hi1);
+        ss0 += a.gx * (fs_lo0 - fs_hi0);
+        ss1 += a.gx * (fs_lo1 - fs_hi1);
         const T pn0 = c0.p + a.dt * (sp0 + react0), pn1 = c1.p + a.dt * (sp1 + react1);
         const T nn0 = c0.n + a.dt * ((a.lambda_np * pn0) * H0), nn1 = c1.n + a.dt * ((a.lambda_np * pn1) * H1);
         const T sn0 = c0.s + a.dt * (ss0 - (a.lambda_s * c0.s) * pn0), sn1 = c1.s + a.dt * (ss1 - (a.lambda_s * c1.s) * pn1);
@@ -509,8 +509,8 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk_step_v4(const StepArgs<T> a,
     VoxFk<T> A0, A1, B0, B1;
     A0.u = u[g.c0]; A0.k = kc[g.c0];
     A1.u = u[g.c1]; A1.k = kc[g.c1];
-    T f_lo0 = relu(kc[g.prev0] + A0.k) * (u[g.prev0] - A0.u);
-    T f_lo1 = relu(kc[g.prev1] + A1.k) * (u[g.prev1] - A1.u);
+    T f_lo0 = relu2(kc[g.prev0] + A0.k) * (u[g.prev0] - A0.u);
+    T f_lo1 = relu2(kc[g.prev1] + A1.k) * (u[g.prev1] - A1.u);
     T hu = 0, hk = 0;
     if (g.ring) { hu = u[g.h]; hk = kc[g.h]; }
     int buf = 0;
@@ -533,17 +533,17 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk_step_v4(const StepArgs<T> a,
             l2_prefetch_strip(u, q, pf.count, pf.total); l2_prefetch_strip(kc, q, pf.count, pf.total);
         }
         const T react0 = a.rho * c0.u * (T(1) - c0.u), react1 = a.rho * c1.u * (T(1) - c1.u);
-        const T f_mid = relu(c0.k + c1.k) * (c0.u - c1.u);
+        const T f_mid = relu2(c0.k + c1.k) * (c0.u - c1.u);
         __syncthreads();
         const Pair<T> up = tl[o0 - RS], dn = tl[o1 + RS];
         const Pair<T> l0 = tl[o0 - 1], r0 = tl[o0 + 1], l1 = tl[o1 - 1], r1 = tl[o1 + 1];
-        T sp0 = a.cy * (relu(up.b + c0.k) * (up.a - c0.u) - f_mid);
-        T sp1 = a.cy * (f_mid - relu(c1.k + dn.b) * (c1.u - dn.a));
-        sp0 += a.cz * (relu(l0.b + c0.k) * (l0.a - c0.u) - relu(c0.k + r0.b) * (c0.u - r0.a));
-        sp1 += a.cz * (relu(l1.b + c1.k) * (l1.a - c1.u) - relu(c1.k + r1.b) * (c1.u - r1.a));
-        const T f_hi0 = relu(c0.k + p0.k) * (c0.u - p0.u), f_hi1 = relu(c1.k + p1.k) * (c1.u - p1.u);
-        sp0 += a.cx * (f_lo0 - f_hi0);
-        sp1 += a.cx * (f_lo1 - f_hi1);
+        T sp0 = a.hy * (relu2(up.b + c0.k) * (up.a - c0.u) - f_mid);
+        T sp1 = a.hy * (f_mid - relu2(c1.k + dn.b) * (c1.u - dn.a));
+        sp0 += a.hz * (relu2(l0.b + c0.k) * (l0.a - c0.u) - relu2(c0.k + r0.b) * (c0.u - r0.a));
+        sp1 += a.hz * (relu2(l1.b + c1.k) * (l1.a - c1.u) - relu2(c1.k + r1.b) * (c1.u - r1.a));
+        const T f_hi0 = relu2(c0.k + p0.k) * (c0.u - p0.u), f_hi1 = relu2(c1.k + p1.k) * (c1.u - p1.u);
+        sp0 += a.hx * (f_lo0 - f_hi0);
+        sp1 += a.hx * (f_lo1 - f_hi1);
         const T un0 = c0.u + a.dt * (sp0 + react0), un1 = c1.u + a.dt * (sp1 + react1);
         const bool cnt = counts(a, x);
         if (g.valid0) { out[g.c0] = un0; if (cnt) s += (double)un0; }
