@@ -252,6 +252,13 @@ int tgtk_sim_download_resampled_async(tgtk_sim *sim, int field, const int32_t lo
                                       const int32_t out_shape[3]);
 int tgtk_sim_segmentation_async(tgtk_sim *sim, const int32_t lo[3], const int32_t virt_shape[3], const int32_t out_shape[3],
                                 double th_necro_n, double th_enhancing_p, double th_edema_p, uint8_t *out);
+/* What Solver.solve() does with the final state and with every recorded snapshot -- restore_tumor + zoom(order=1),
+ * FK/FK.py:229-238 -- for `count` volumes in one call: snapshots [first, first + count) of `field` (first = -1, count = 1:
+ * the current state) are resampled on the device straight from their arenas, copied through a ring of page-locked
+ * staging buffers and written to `out` (count consecutive dense float64 volumes of out_shape, ordinary pageable memory,
+ * e.g. a fresh numpy array) by several host threads while the next volume is in flight.  Synchronous. */
+int tgtk_sim_fetch_series(tgtk_sim *sim, int field, int first, int count, const int32_t lo[3], const int32_t virt_shape[3],
+                          const int32_t out_shape[3], double *out);
 /* Page-locked host memory for the buffers of the host-pointer entry points (NULL on failure). */
 void *tgtk_host_alloc(size_t bytes);
 void tgtk_host_free(void *ptr);

@@ -47,3 +47,8 @@ def gold_atlas():
 @pytest.fixture(scope="session")
 def atlas_labels():
     return np.load(os.path.join(GOLD, "sri_tissue_labels.npz"))["seg"]
+
+
+@pytest.fixture(scope="session")
+def gold_atlas_dti():
+    return np.load(os.path.join(GOLD, "atlas_dti_res05.npz"))

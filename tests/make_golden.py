@@ -14,6 +14,7 @@ Groups
   solve  whole solve() calls of the three solvers on a small synthetic phantom
          (result dict arrays, step counts, stop criteria; finite stopping_volume; seed
          outside the brain; time series).
+  dti_atlas  FK_DTI_Solver.solve() of the reference on the synthetic tensor volume of SURVEY.md 8(d) input 3 at res 0.5.
   atlas  the bundled SRI label atlas (240x240x155) packed to uint8, and reference loop
          results on it at resolution_factor 0.5 (FK 300 steps, FK_2c 560 steps) obtained by
          calling the reference's own update methods on the reference's own cropped arrays.
@@ -322,6 +323,40 @@ def gen_atlas():
     print("atlas_res05.npz", os.path.getsize(os.path.join(GOLD, "atlas_res05.npz")))
 
 
+def gen_dti_atlas():
+    """SURVEY.md 8(d) input 3 / VERDICT r1 item 10: the synthetic FSL_HCP1065-shaped lower-6 tensor volume on the SRI
+    label atlas -> tools.get_tensor_from_lower6 -> FK_DTI_Solver.solve() of the unmodified reference with the
+    FK_DTI_example.ipynb parameters at resolution_factor 0.5, once with the notebook's stop criterion
+    (stopping_volume 15000, stopping_time 1000) and once as the fixed-step variant (stopping_time 100).  The
+    full-resolution final states (71 MB each) are stored sub-sampled by 2 per axis plus three digests of the full array."""
+    from tumorgrowthtoolkit_b200 import synthetic
+    FK, FK2c, DTI, tools = import_reference()
+    seg = np.load(os.path.join(GOLD, "sri_tissue_labels.npz"))["seg"]
+    lower6 = synthetic.dti_lower6_field(seg)
+    tensors = tools.get_tensor_from_lower6(lower6)
+    pct = synthetic.seed_inside(seg == 3, (0.49, 0.30, 0.7))
+    out = {"seed_pct": np.array(pct)}
+    base = dict(Dw=1.0, rho=0.2, diffusionEllipsoidScaling=1, diffusionTensors=tensors, NxT1_pct=pct[0], NyT1_pct=pct[1],
+                NzT1_pct=pct[2], resolution_factor=0.5, verbose=True)
+    cases = {"stop": dict(init_scale=0.1, stopping_volume=15000, stopping_time=1000),
+             "fixed": dict(init_scale=1.0, stopping_time=100)}
+    for name, extra in cases.items():
+        t = time.time()
+        res = DTI(dict(base, **extra)).solve()
+        print("atlas DTI", name, f"{time.time() - t:.1f}s", _scalars(res))
+        assert res["success"], res
+        fs = res["final_state"]
+        w = np.cos(0.37 * np.arange(fs.size)).reshape(fs.shape)
+        out[name + "/final_state_sub2"] = np.ascontiguousarray(fs[::2, ::2, ::2])
+        out[name + "/final_state_digest"] = np.array([fs.sum(), (fs * fs).sum(), (fs * w).sum()])
+        out[name + "/final_time"] = np.array(res["final_time"])
+        out[name + "/final_volume"] = np.array(res["final_volume"])
+        out[name + "/stopping_criteria"] = np.array(res["stopping_criteria"])
+        out[name + "/initial_state_digest"] = np.array([res["initial_state"].sum(), (res["initial_state"] ** 2).sum()])
+    np.savez_compressed(os.path.join(GOLD, "atlas_dti_res05.npz"), **out)
+    print("atlas_dti_res05.npz", os.path.getsize(os.path.join(GOLD, "atlas_dti_res05.npz")))
+
+
 def elongate_inputs():
     """Seeded (6,7,5,3,3) tensor field for the elongation (tools.py:109-164): SPD tensors with separated
     eigenvalues, isotropic and axis-aligned degenerate tensors, zeros (background)."""
@@ -352,6 +387,6 @@ def gen_elongate():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    groups = sys.argv[1:] or ["ops", "solve", "atlas", "elongate"]
+    groups = sys.argv[1:] or ["ops", "solve", "atlas", "elongate", "dti_atlas"]
     for g in groups:
-        {"ops": gen_ops, "solve": gen_solve, "atlas": gen_atlas, "elongate": gen_elongate}[g]()
+        {"ops": gen_ops, "solve": gen_solve, "atlas": gen_atlas, "elongate": gen_elongate, "dti_atlas": gen_dti_atlas}[g]()

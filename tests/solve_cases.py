@@ -106,3 +106,44 @@ def compare_result(name, res, gold, tol, vol_rtol=1e-9):
                 assert abs(float(v) - float(want)) <= vol_rtol * max(1.0, abs(float(want))), (k, v, want)
             else:
                 _cmp_array(f"{name}/{k}", v, want, tol)
+
+
+# ---- SURVEY.md 8(d) input 3: FK_DTI on the synthetic tensor volume over the SRI atlas (tests/golden/atlas_dti_res05.npz) ----
+ATLAS_DTI_CASES = {"stop": dict(init_scale=0.1, stopping_volume=15000, stopping_time=1000),
+                   "fixed": dict(init_scale=1.0, stopping_time=100)}
+_atlas_dti_tensors = {}
+
+
+def atlas_dti_params(labels, gold, case):
+    """Parameters of tests/make_golden.py:gen_dti_atlas (the synthetic tensor volume is regenerated, seeded)."""
+    import contextlib, io
+    from tumorgrowthtoolkit_b200 import synthetic
+    from tumorgrowthtoolkit_b200.FK_DTI import tools
+    if "T" not in _atlas_dti_tensors:
+        with contextlib.redirect_stdout(io.StringIO()):
+            _atlas_dti_tensors["T"] = tools.get_tensor_from_lower6(synthetic.dti_lower6_field(labels))
+    pct = synthetic.seed_inside(labels == 3, (0.49, 0.30, 0.7))
+    assert np.allclose(pct, gold["seed_pct"])
+    p = dict(Dw=1.0, rho=0.2, diffusionEllipsoidScaling=1, diffusionTensors=_atlas_dti_tensors["T"], NxT1_pct=pct[0], NyT1_pct=pct[1],
+             NzT1_pct=pct[2], resolution_factor=0.5)
+    p.update(ATLAS_DTI_CASES[case])
+    return p
+
+
+def compare_atlas_dti(case, res, gold, tol):
+    assert res["success"], res.get("error")
+    assert str(res["stopping_criteria"]) == str(gold[case + "/stopping_criteria"])
+    assert float(res["final_time"]) == float(gold[case + "/final_time"])        # same stop step, same dt
+    fv = float(gold[case + "/final_volume"])
+    assert abs(float(res["final_volume"]) - fv) <= max(tol, 1e-9) * fv
+    fs = res["final_state"]
+    assert fs.shape == (240, 240, 155)
+    err = float(np.max(np.abs(fs[::2, ::2, ::2] - gold[case + "/final_state_sub2"])))
+    assert err <= tol, err
+    w = np.cos(0.37 * np.arange(fs.size)).reshape(fs.shape)
+    dg = gold[case + "/final_state_digest"]
+    d = np.array([fs.sum(), (fs * fs).sum(), (fs * w).sum()])
+    assert np.max(np.abs(d - dg) / np.maximum(np.abs(dg), 1.0)) <= tol * 1e3
+    ini = res["initial_state"]
+    di = gold[case + "/initial_state_digest"]
+    assert abs(ini.sum() - di[0]) <= 1e-9 * max(1.0, di[0]) and abs((ini ** 2).sum() - di[1]) <= 1e-9 * max(1.0, di[1])

@@ -10,13 +10,14 @@ from tumorgrowthtoolkit_b200 import _loop
 from tumorgrowthtoolkit_b200.FK import Solver as FK
 from tumorgrowthtoolkit_b200.FK_2c import Solver as FK2c
 from tumorgrowthtoolkit_b200.FK_DTI import FK_DTI_Solver as DTI
-from tests.solve_cases import FK_CASES, C2_CASES, DTI_CASES, base_params, dti_params, compare_result
+from tests.solve_cases import (FK_CASES, C2_CASES, DTI_CASES, base_params, dti_params, compare_result, atlas_dti_params,
+                               compare_atlas_dti)
 
 
 @pytest.fixture()
 def cpu_loops(monkeypatch, oracle):
     def drop(kw):
-        for k in ("precision", "device", "bit_exact", "devices"):
+        for k in ("precision", "device", "bit_exact", "devices", "output"):
             kw.pop(k, None)
         return kw
     monkeypatch.setattr(_loop, "fk_loop", lambda *a, **kw: oracle.fk_loop(*a, **drop(kw)))
@@ -54,6 +55,13 @@ def test_dti_solve_host_logic(name, gold_solve, cpu_loops):
     p["elongation_backend"] = "torch"              # no GPU here: the literal restatement of the reference's CPU eigh
     res = DTI(p).solve()
     compare_result(name, res, gold_solve, tol=tol)
+
+
+def test_atlas_dti_solve_host_logic(atlas_labels, gold_atlas_dti, cpu_loops):
+    """The config-3 input through the solver mirror with the oracle's loop: resample of the 4-D rgb volume, seed
+    re-picked inside WM, step-count law on the full-resolution maximum, the notebook's stopping_volume."""
+    res = DTI(atlas_dti_params(atlas_labels, gold_atlas_dti, "stop")).solve()
+    compare_atlas_dti("stop", res, gold_atlas_dti, 1e-10)
 
 
 def test_rgb_from_tensor_matches_reference(gold_solve):

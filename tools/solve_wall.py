@@ -22,12 +22,39 @@ T = synthetic.dti_tensor_field(wm, gm)
 cases.append(("FK_DTI res 1.0, stopping_volume 15000 (FK_DTI_example.ipynb)", DTI,
               dict(Dw=1.0, rho=0.2, init_scale=0.1, diffusionEllipsoidScaling=1, stopping_volume=15000, stopping_time=1000,
                    diffusionTensors=T, resolution_factor=1.0, NxT1_pct=0.49, NyT1_pct=0.30, NzT1_pct=0.7)))
+# where the wall time of a solve() goes: wrap the host-side stages
+import functools
+from tumorgrowthtoolkit_b200 import _host, _loop
+from tumorgrowthtoolkit_b200.FK_DTI import tools as dti_tools
+PHASES = {}
+
+
+def _timed(mod, fn, label):
+    orig = getattr(mod, fn)
+
+    @functools.wraps(orig)
+    def wrapper(*a, **k):
+        t = time.perf_counter()
+        try:
+            return orig(*a, **k)
+        finally:
+            PHASES[label] = PHASES.get(label, 0.0) + time.perf_counter() - t
+    setattr(mod, fn, wrapper)
+
+
+for mod, fn, label in ((_host, "resample_linear", "resample in"), (_host, "seed_gaussian", "seed"), (_host, "bounding_box", "bbox"),
+                       (_loop, "fk_loop", "loop+outputs"), (_loop, "fk2c_loop", "loop+outputs"), (_loop, "dti_loop", "loop+outputs"),
+                       (dti_tools, "makeXYZ_rgb_from_tensor", "rgb from tensor"), (_host.LowResGrid, "upsample", "upsample initial")):
+    _timed(mod, fn, label)
+
 for name, cls, p in cases:
     for rep in range(2):
+        PHASES.clear()
         s = cls(dict(p))
         t0 = time.perf_counter()
         res = s.solve()
         wall = time.perf_counter() - t0
     st = getattr(s, "last_loop_stats", {})
     print(f"{name}: solve() {wall:.2f} s, loop {st.get('loop_ms', float('nan')) / 1e3:.3f} s for {st.get('steps_run')} steps on "
-          f"{st.get('voxels')} voxels, success={res.get('success')}, final_volume={res.get('final_volume')}", flush=True)
+          f"{st.get('voxels')} voxels, success={res.get('success')}, final_volume={res.get('final_volume')}; phases "
+          + ", ".join(f"{k} {v:.3f}" for k, v in PHASES.items()), flush=True)

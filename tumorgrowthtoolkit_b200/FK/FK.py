@@ -17,6 +17,33 @@ from .. import _host, _loop, _ops
 from ..base_solver import BaseSolver
 
 
+def _full_state(run, grid, box, device, key=None):
+    """The loop's final state on the input grid (FK.py:229-238): resampled on the device by the loop itself when it could
+    (`state_full`), otherwise -- slab-decomposed runs, a test double standing in for the loop in the host-logic tests --
+    restore + zoom of the cropped low-resolution array."""
+    if run.get('state_full') is not None:
+        return run['state_full'] if key is None else run['state_full'][key]
+    return grid.upsample_crop(run['state'] if key is None else run['state'][key], box, device=device)
+
+
+def _full_series(run, grid, box, device, key=None):
+    """The recorded snapshots on the input grid, as the (n, X, Y, Z) array FK.py:238 builds."""
+    if run.get('snapshots_full') is not None:
+        arr = run['snapshots_full'] if key is None else run['snapshots_full'][key]
+        return arr if len(arr) else np.array([])
+    snaps = run['snapshots'] if key is None else run['snapshots'][key]
+    return np.array([grid.upsample_crop(s, box, device=device) for s in snaps])
+
+
+def _loop_stats(run):
+    """Not part of the reference's result dict: kept on the solver instance for benchmarks."""
+    st = run['state'] if run.get('state') is not None else None
+    if isinstance(st, dict):
+        st = st['P']
+    voxels = run.get('voxels') or (int(np.prod(st.shape)) if st is not None else None)
+    return {'steps_run': run['steps_run'], 'loop_ms': run.get('loop_ms'), 'voxels': voxels}
+
+
 class Solver(BaseSolver):
     def __init__(self, params):
         super().__init__(params)
@@ -115,24 +142,23 @@ class Solver(BaseSolver):
                                 th_matter, Dw, ratio, rho, dt, dx, dy, dz, nsteps,
                                 stopping_volume=stopping_volume, record_steps=record,
                                 precision=p.get('precision', 'fp64'), device=self._device(),
-                                bit_exact=bool(p.get('bit_exact', False)), devices=p.get('devices'))
+                                bit_exact=bool(p.get('bit_exact', False)), devices=p.get('devices'),
+                                output=grid.output_spec(box))
             volume = np.float64(run['volume'])
             final_time = run['t_stop'] * dt if run['stop'] == 'volume' else stopping_time
 
             result['initial_state'] = grid.upsample(initial, device=self._device())
-            result['final_state'] = grid.upsample_crop(run['state'], box, device=self._device())
+            result['final_state'] = _full_state(run, grid, box, self._device())
             result['final_time'] = final_time
             result['final_volume'] = volume
             result['stopping_criteria'] = 'volume' if volume >= stopping_volume else 'time'
-            result['time_series'] = (np.array([grid.upsample_crop(s, box, device=self._device())
-                                               for s in run['snapshots']]) if record is not None else None)
+            result['time_series'] = _full_series(run, grid, box, self._device()) if record is not None else None
             result['Dw'] = Dw
             result['rho'] = rho
             result['success'] = True
             result['NxT1_pct'], result['NyT1_pct'], result['NzT1_pct'] = pct
             # not part of the reference's result dict: kept on the instance for benchmarks
-            self.last_loop_stats = {'steps_run': run['steps_run'], 'loop_ms': run.get('loop_ms'),
-                                    'voxels': int(np.prod(run['state'].shape))}
+            self.last_loop_stats = _loop_stats(run)
         except Exception as e:                                        # FK.py:246-248
             result['error'] = str(e)
             result['success'] = False

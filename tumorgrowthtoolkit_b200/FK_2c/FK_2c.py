@@ -8,7 +8,7 @@ Optional extra parameters: precision ('fp64' | 'fp32'), device.
 import numpy as np
 
 from .. import _host, _loop, _ops
-from ..FK.FK import Solver as FK_Solver
+from ..FK.FK import Solver as FK_Solver, _full_state, _full_series, _loop_stats
 
 
 class Solver(FK_Solver):
@@ -88,16 +88,16 @@ class Solver(FK_Solver):
                               _host.crop(initial['S'], box), _host.crop(wm_lo, box), _host.crop(gm_lo, box),
                               th_matter, th_necro, Dw, ratio, D_s, rho, lambda_np, sigma_np, lambda_s,
                               dt, dx, dy, dz, nsteps, stopping_volume=stopping_volume, record_steps=record,
-                              precision=p.get('precision', 'fp64'), device=self._device(), devices=p.get('devices'))
+                              precision=p.get('precision', 'fp64'), device=self._device(), devices=p.get('devices'),
+                              output=grid.output_spec(box))
         volume = np.float64(run['volume'])
         final_time = run['t_stop'] * dt if run['stop'] == 'volume' else stopping_time
 
         result = {}
         result['initial_state'] = {k: grid.upsample(v, device=self._device()) for k, v in initial.items()}
-        result['final_state'] = {k: grid.upsample_crop(run['state'][k], box, device=self._device()) for k in 'PNS'}
+        result['final_state'] = {k: _full_state(run, grid, box, self._device(), k) for k in 'PNS'}
         if record is not None:
-            result['time_series'] = {k: [grid.upsample_crop(s, box, device=self._device()) for s in run['snapshots'][k]]
-                                     for k in 'PNS'}
+            result['time_series'] = {k: list(_full_series(run, grid, box, self._device(), k)) for k in 'PNS'}
         else:
             result['time_series'] = None
         result['Dw'] = Dw
@@ -107,6 +107,5 @@ class Solver(FK_Solver):
         result['final_time'] = final_time
         result['final_volume'] = volume
         result['stopping_criteria'] = 'volume' if volume >= stopping_volume else 'time'
-        self.last_loop_stats = {'steps_run': run['steps_run'], 'loop_ms': run.get('loop_ms'),
-                                'voxels': int(np.prod(run['state']['P'].shape))}
+        self.last_loop_stats = _loop_stats(run)
         return result

@@ -11,7 +11,7 @@ reference parity; with zero off-diagonals it equals the reference operator bit f
 import numpy as np
 
 from .. import _host, _loop
-from ..FK.FK import Solver as FK_Solver
+from ..FK.FK import Solver as FK_Solver, _full_state, _full_series, _loop_stats
 from . import tools
 
 
@@ -104,28 +104,27 @@ class FK_DTI_Solver(FK_Solver):
                 run = _loop.dti_full_loop(_host.crop(initial, box), _host.crop(rgb_lo, box), _host.crop(off_lo, box),
                                           Dw, rho, dt, dx, dy, dz, nsteps, stopping_volume=stopping_volume,
                                           record_steps=record, precision=p.get('precision', 'fp64'),
-                                          device=self._device())
+                                          device=self._device(), output=grid.output_spec(box))
             else:
                 run = _loop.dti_loop(_host.crop(initial, box), _host.crop(rgb_lo, box), Dw, rho, dt, dx, dy, dz, nsteps,
                                      stopping_volume=stopping_volume, record_steps=record,
-                                     precision=p.get('precision', 'fp64'), device=self._device(), devices=p.get('devices'))
+                                     precision=p.get('precision', 'fp64'), device=self._device(), devices=p.get('devices'),
+                                     output=grid.output_spec(box))
             if run['stop'] == 'small':
                 print("Volume is to small")                             # FK_DTI.py:203-206 (sic)
             volume = np.float64(run['volume'])
             final_time = run['t_stop'] * dt if run['stop'] == 'volume' else stopping_time
 
             result['initial_state'] = grid.upsample(initial, device=self._device())
-            result['final_state'] = grid.upsample_crop(run['state'], box, device=self._device())
+            result['final_state'] = _full_state(run, grid, box, self._device())
             result['final_time'] = final_time
             result['final_volume'] = volume
             result['stopping_criteria'] = 'volume' if volume >= stopping_volume else 'time'
-            result['time_series'] = (np.array([grid.upsample_crop(s, box, device=self._device())
-                                               for s in run['snapshots']]) if record is not None else None)
+            result['time_series'] = _full_series(run, grid, box, self._device()) if record is not None else None
             result['Dw'] = Dw
             result['rho'] = rho
             result['success'] = True        # also after the "too small" exit, as in FK_DTI.py:229
-            self.last_loop_stats = {'steps_run': run['steps_run'], 'loop_ms': run.get('loop_ms'),
-                                    'voxels': int(np.prod(run['state'].shape))}
+            self.last_loop_stats = _loop_stats(run)
         except Exception as e:              # FK_DTI.py:232-235
             print(e)
             result['error'] = str(e)

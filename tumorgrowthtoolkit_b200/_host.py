@@ -52,6 +52,10 @@ class LowResGrid:
     def upsample(self, a, device=0):
         return np.array(resample_linear(a, self.up_factor, device=device))
 
+    def output_spec(self, box):
+        """(lo, virt_shape, out_shape) of restore_tumor + zoom back to the input grid, for the device-side output path."""
+        return box[0], self.shape, _out_shape(self.shape, self.up_factor)
+
     def upsample_crop(self, crop_arr, box, device=0):
         """restore_tumor + zoom back to the input grid in one device pass (FK.py:229-238)."""
         return _device_resample(crop_arr, _out_shape(self.shape, self.up_factor), lo=box[0], virt_shape=self.shape,

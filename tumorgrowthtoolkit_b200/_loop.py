@@ -28,18 +28,37 @@ def dtype_code(precision):
         raise ValueError(f"precision must be 'fp64' or 'fp32', got {precision!r}") from None
 
 
-def _finish(sim, nsteps, record_steps, fields, names):
+def _finish(sim, nsteps, record_steps, fields, names, output=None):
+    """Runs the loop and collects its results.  `output` = (lo, virt_shape, out_shape): what solve() does with the final
+    state and with every snapshot -- restore_tumor into the low-resolution grid and zoom back to the input grid,
+    FK/FK.py:229-238 -- happens on the device while the simulation is still open (tgtk_sim_fetch_series); the result then
+    carries 'state_full' / 'snapshots_full' instead of the cropped low-resolution arrays."""
     sim.run(nsteps, record_steps)
     st = sim.sync()
+    stop = {nat.STOP_NONE: "time", nat.STOP_VOLUME: "volume", nat.STOP_SMALL: "small"}[st.stop_reason]
+    res = dict(volume=(float(st.last_volume) if st.steps_run > 0 else None),
+               steps_run=int(st.steps_run), stop=stop,
+               t_stop=(int(st.stop_step) if st.stop_reason == nat.STOP_VOLUME else None),
+               loop_ms=float(st.loop_ms), launches=int(st.kernel_launches), voxels=int(np.prod(sim.shape)))
+    if output is not None:
+        lo, virt_shape, out_shape = output
+        out_shape = tuple(int(v) for v in out_shape)
+        full = {n: sim.fetch_series(f, -1, 1, lo, virt_shape, np.empty(out_shape)) for n, f in zip(names, fields)}
+        snaps_full = None
+        if record_steps is not None:
+            snaps_full = {n: sim.fetch_series(f, 0, st.snapshots, lo, virt_shape, np.empty((st.snapshots,) + out_shape))
+                          for n, f in zip(names, fields)}
+        res.update(state=None, snapshots=None, state_full=full, snapshots_full=snaps_full)
+        if len(names) == 1:
+            res["state_full"] = full[names[0]]
+            if snaps_full is not None:
+                res["snapshots_full"] = snaps_full[names[0]]
+        return res
     state = {n: sim.download(f) for n, f in zip(names, fields)}
     snaps = None
     if record_steps is not None:
         snaps = {n: [sim.snapshot(i, f) for i in range(st.snapshots)] for n, f in zip(names, fields)}
-    stop = {nat.STOP_NONE: "time", nat.STOP_VOLUME: "volume", nat.STOP_SMALL: "small"}[st.stop_reason]
-    res = dict(state=state, volume=(float(st.last_volume) if st.steps_run > 0 else None),
-               steps_run=int(st.steps_run), stop=stop,
-               t_stop=(int(st.stop_step) if st.stop_reason == nat.STOP_VOLUME else None),
-               snapshots=snaps, loop_ms=float(st.loop_ms), launches=int(st.kernel_launches))
+    res.update(state=state, snapshots=snaps)
     if len(names) == 1:
         res["state"] = state[names[0]]
         if snaps is not None:
@@ -62,7 +81,7 @@ def _slab_requested(devices):
 
 
 def fk_loop(u0, WM, GM, th, Dw, ratio, rho, dt, dx, dy, dz, nsteps, stopping_volume=np.inf,
-            record_steps=None, precision="fp64", device=0, bit_exact=False, devices=None):
+            record_steps=None, precision="fp64", device=0, bit_exact=False, devices=None, output=None):
     """FK: get_D (FK.py:200) fused into the step kernel + the loop of FK.py:212-226.
     bit_exact=True builds the three face arrays in the reference's rounding order and steps
     them with unfused arithmetic (fp64 results then equal numpy's bit for bit)."""
@@ -82,11 +101,11 @@ def fk_loop(u0, WM, GM, th, Dw, ratio, rho, dt, dx, dy, dz, nsteps, stopping_vol
         sim.upload(nat.FIELD_GM, GM)
         sim.upload(nat.FIELD_U, u0)
         sim.prepare()
-        return _finish(sim, nsteps, record_steps, (nat.FIELD_U,), ("u",))
+        return _finish(sim, nsteps, record_steps, (nat.FIELD_U,), ("u",), output)
 
 
 def dti_loop(u0, rgb, Dw, rho, dt, dx, dy, dz, nsteps, stopping_volume=np.inf, record_steps=None,
-             precision="fp64", device=0, devices=None):
+             precision="fp64", device=0, devices=None, output=None):
     """FK_DTI: get_D_from_DTI (FK_DTI.py:174: D_a = rgb[...,a]*Dw, D_plus aliasing D_minus)
     + the loop of FK_DTI.py:195-214 incl. the `volume < 1e-6` exit."""
     if _slab_requested(devices):
@@ -101,11 +120,11 @@ def dti_loop(u0, rgb, Dw, rho, dt, dx, dy, dz, nsteps, stopping_volume=np.inf, r
             sim.upload(nat.FIELD_COEF0 + a, rgb[..., a] * Dw)
         sim.upload(nat.FIELD_U, u0)
         sim.prepare()
-        return _finish(sim, nsteps, record_steps, (nat.FIELD_U,), ("u",))
+        return _finish(sim, nsteps, record_steps, (nat.FIELD_U,), ("u",), output)
 
 
 def dti_full_loop(u0, rgb, offdiag, Dw, rho, dt, dx, dy, dz, nsteps, stopping_volume=np.inf, record_steps=None,
-                  precision="fp64", device=0):
+                  precision="fp64", device=0, output=None):
     """Opt-in full-tensor FK_DTI (NOT in the packaged reference, SURVEY.md finding 1): the
     reference's diagonal operator plus 2*sum_{a<b} D_ab d_a d_b u on a 19-point stencil.
     rgb[...,a] = normalised D_aa as in dti_loop; offdiag[...,(xy,xz,yz)] in the same units."""
@@ -118,11 +137,12 @@ def dti_full_loop(u0, rgb, offdiag, Dw, rho, dt, dx, dy, dz, nsteps, stopping_vo
             sim.upload(nat.FIELD_COEF0 + 3 + a, offdiag[..., a] * Dw)
         sim.upload(nat.FIELD_U, u0)
         sim.prepare()
-        return _finish(sim, nsteps, record_steps, (nat.FIELD_U,), ("u",))
+        return _finish(sim, nsteps, record_steps, (nat.FIELD_U,), ("u",), output)
 
 
 def fk2c_loop(P0, N0, S0, WM, GM, th, th_necro, Dw, ratio, Ds, rho, lambda_np, sigma_np, lambda_s,
-              dt, dx, dy, dz, nsteps, stopping_volume=np.inf, record_steps=None, precision="fp64", device=0, devices=None):
+              dt, dx, dy, dz, nsteps, stopping_volume=np.inf, record_steps=None, precision="fp64", device=0, devices=None,
+              output=None):
     """FK_2c: get_D_with_necro + get_D(...,D_s,1) + FK_2c_update fused per step
     (FK_2c.py:215-216,229-230) + the loop of FK_2c.py:227-245."""
     if _slab_requested(devices):
@@ -140,4 +160,4 @@ def fk2c_loop(P0, N0, S0, WM, GM, th, th_necro, Dw, ratio, Ds, rho, lambda_np, s
         sim.upload(nat.FIELD_N, N0)
         sim.upload(nat.FIELD_S, S0)
         sim.prepare()
-        return _finish(sim, nsteps, record_steps, (nat.FIELD_P, nat.FIELD_N, nat.FIELD_S), ("P", "N", "S"))
+        return _finish(sim, nsteps, record_steps, (nat.FIELD_P, nat.FIELD_N, nat.FIELD_S), ("P", "N", "S"), output)

@@ -89,6 +89,7 @@ def lib():
     i3p = ctypes.POINTER(ctypes.c_int32 * 3)
     L.tgtk_sim_download_resampled_async.argtypes = [vp, ctypes.c_int, i3p, i3p, ctypes.c_void_p, i3p]
     L.tgtk_sim_segmentation_async.argtypes = [vp, i3p, i3p, i3p, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_void_p]
+    L.tgtk_sim_fetch_series.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, i3p, i3p, i3p, ctypes.c_void_p]
     L.tgtk_host_alloc.argtypes = [ctypes.c_size_t]
     L.tgtk_host_alloc.restype = ctypes.c_void_p
     L.tgtk_host_free.argtypes = [ctypes.c_void_p]
@@ -305,6 +306,19 @@ class Sim:
         _check(lib().tgtk_sim_download_resampled_async(self._h, int(field), ctypes.byref(i3(*[int(v) for v in lo])),
                                                        ctypes.byref(i3(*[int(v) for v in virt_shape])), out.ctypes.data,
                                                        ctypes.byref(i3(*out.shape))))
+        return out
+
+    def fetch_series(self, field, first, count, lo, virt_shape, out):
+        """restore_tumor + zoom(order=1) of snapshots [first, first + count) of `field` (first = -1, count = 1: the current
+        state) into `out` (float64, C-contiguous, (count, X, Y, Z) or (X, Y, Z)): resampled on the device, staged through
+        page-locked buffers, written by several host threads.  Returns `out`."""
+        i3 = ctypes.c_int32 * 3
+        assert out.dtype == np.float64 and out.flags.c_contiguous
+        shape = out.shape[-3:]
+        assert out.size == int(count) * int(np.prod(shape, dtype=np.int64))
+        _check(lib().tgtk_sim_fetch_series(self._h, int(field), int(first), int(count), ctypes.byref(i3(*[int(v) for v in lo])),
+                                           ctypes.byref(i3(*[int(v) for v in virt_shape])), ctypes.byref(i3(*[int(v) for v in shape])),
+                                           out.ctypes.data))
         return out
 
     def segmentation_async(self, lo, virt_shape, th_necro_n, th_enhancing_p, th_edema_p, out):

@@ -8,6 +8,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/tgtk_b200.h"
@@ -1833,6 +1834,109 @@ int tgtk_sim_segmentation_async(tgtk_sim *s, const int32_t lo[3], const int32_t 
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, s->seg_out, nout, cudaMemcpyDeviceToHost, s->stream));
     return 0;
+}
+
+// ---- batched restore + zoom of snapshots / the final state into pageable host memory ------------------------------
+namespace {
+struct PinnedRing {            // page-locked staging buffers, kept for the life of the process (page-locking 71 MB costs ~25 ms)
+    std::mutex mu;
+    void *buf[3] = {nullptr, nullptr, nullptr};
+    size_t bytes = 0;
+    bool busy = false;
+};
+PinnedRing g_ring;
+
+// dst[0..n) = src[0..n) with `nthreads` threads: a fresh numpy array is untouched memory, one thread spends more time
+// in page faults than in the copy
+void parallel_copy(char *dst, const char *src, size_t n, int nthreads, std::vector<std::thread> &pool)
+{
+    const size_t chunk = ((n / nthreads) + 4095) & ~(size_t)4095;
+    for (size_t off = 0; off < n; off += chunk) {
+        const size_t len = std::min(chunk, n - off);
+        pool.emplace_back([=] { memcpy(dst + off, src + off, len); });
+    }
+}
+}  // namespace
+
+int tgtk_sim_fetch_series(tgtk_sim *s, int field, int first, int count, const int32_t lo[3], const int32_t virt_shape[3],
+                          const int32_t out_shape[3], double *out)
+{
+    if (!s || !lo || !virt_shape || !out_shape || !out) return fail("tgtk_sim_fetch_series", "null argument");
+    if (field < 0 || field >= s->nfields) return fail("tgtk_sim_fetch_series", "not a state field of this model");
+    if (count < 0 || first < -1 || (first == -1 && count > 1) || (first >= 0 && first + count > (int)s->snaps.size()))
+        return fail("tgtk_sim_fetch_series", "no such snapshot");
+    if (count == 0) return 0;
+    ResampleGeom g;
+    if (resample_geom(s, "tgtk_sim_fetch_series", lo, virt_shape, out_shape, g)) return 1;
+    CU(cudaSetDevice(s->device));
+    if (!s->ctrl_valid && fetch_ctrl(s)) return 1;
+    const size_t nout = (size_t)g.OX * g.OY * g.OZ, bytes = nout * 8, state_bytes = (size_t)s->p.X * s->sx * s->elem;
+    // two device output buffers, so that the resample of item i+1 does not wait for the copy of item i
+    for (int k = 0; k < 2; ++k)
+        if (nout > s->resample_async_cap[k] || !s->resample_async[k]) {
+            if (s->resample_async[k]) CU(sim_free(s, s->resample_async[k]));
+            s->resample_async[k] = nullptr;
+            s->resample_async_cap[k] = 0;
+            CU(sim_malloc(s, (void **)(&s->resample_async[k]), bytes));
+            s->resample_async_cap[k] = nout;
+        }
+    // the staging ring is process-wide; a concurrent caller (another simulation's thread) falls back to its own buffers
+    bool own_ring = false;
+    void *ring[3] = {nullptr, nullptr, nullptr};
+    {
+        std::lock_guard<std::mutex> lk(g_ring.mu);
+        if (!g_ring.busy) {
+            if (g_ring.bytes < bytes) {
+                for (int k = 0; k < 3; ++k) { if (g_ring.buf[k]) cudaFreeHost(g_ring.buf[k]); g_ring.buf[k] = nullptr; }
+                g_ring.bytes = 0;
+                bool ok = true;
+                for (int k = 0; k < 3 && ok; ++k) ok = (cudaMallocHost(&g_ring.buf[k], bytes) == cudaSuccess);
+                if (ok) g_ring.bytes = bytes;
+            }
+            if (g_ring.bytes >= bytes) { g_ring.busy = true; for (int k = 0; k < 3; ++k) ring[k] = g_ring.buf[k]; }
+        }
+    }
+    if (!ring[0]) {
+        own_ring = true;
+        for (int k = 0; k < 3; ++k)
+            if (cudaMallocHost(&ring[k], bytes) != cudaSuccess) {
+                for (int j = 0; j < k; ++j) cudaFreeHost(ring[j]);
+                return fail("tgtk_sim_fetch_series", "cannot allocate page-locked staging buffers");
+            }
+    }
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    int rc = 0;
+    for (int k = 0; k < 3 && !rc; ++k)
+        if (cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess) rc = fail("tgtk_sim_fetch_series", "cudaEventCreate failed");
+    const int nthreads = std::max(1, std::min(8, (int)std::thread::hardware_concurrency()));
+    std::vector<std::thread> jobs[3];
+    auto join_slot = [&](int k) { for (auto &t : jobs[k]) t.join(); jobs[k].clear(); };
+    auto enqueue = [&](int i) -> int {         // resample item i on the device, copy it into ring slot i % 3
+        const int k = i % 3;
+        join_slot(k);                            // the copy-out that last read this slot
+        const void *src = (first < 0) ? s->state[current_buf(s, nullptr)][field] : (const void *)((char *)s->snaps[first + i] + state_bytes * field);
+        double *dev = s->resample_async[i & 1];
+        if (s->p.dtype == TGTK_F64) resample_state_kernel<double><<<grid_1d(nout), 256, 0, s->stream>>>((const double *)src, g, dev);
+        else resample_state_kernel<float><<<grid_1d(nout), 256, 0, s->stream>>>((const float *)src, g, dev);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(ring[k], dev, bytes, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaEventRecord(ev[k], s->stream));
+        return 0;
+    };
+    if (!rc) rc = enqueue(0);
+    for (int i = 0; i < count && !rc; ++i) {
+        if (i + 1 < count) rc = enqueue(i + 1);
+        if (rc) break;
+        const int k = i % 3;
+        if (cudaEventSynchronize(ev[k]) != cudaSuccess) { rc = fail("tgtk_sim_fetch_series", "device-to-host copy failed"); break; }
+        parallel_copy((char *)(out + (size_t)i * nout), (const char *)ring[k], bytes, nthreads, jobs[k]);
+    }
+    for (int k = 0; k < 3; ++k) join_slot(k);
+    cudaStreamSynchronize(s->stream);
+    for (int k = 0; k < 3; ++k) if (ev[k]) cudaEventDestroy(ev[k]);
+    if (own_ring) { for (int k = 0; k < 3; ++k) cudaFreeHost(ring[k]); }
+    else { std::lock_guard<std::mutex> lk(g_ring.mu); g_ring.busy = false; }
+    return rc;
 }
 
 void *tgtk_host_alloc(size_t bytes)
