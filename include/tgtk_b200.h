@@ -271,6 +271,13 @@ void tgtk_host_free(void *ptr);
 int tgtk_resample_linear_host(int device, const double *in, const int64_t in_strides[3], const int32_t in_shape[3],
                               const int32_t lo[3], const int32_t virt_shape[3], double *out, const int32_t out_shape[3]);
 
+/* tools.makeXYZ_rgb_from_tensor (TumorGrowthToolkit/FK_DTI/tools.py:166-187; FK_DTI_Solver.solve calls it on the whole
+ * (240,240,155,3,3) volume before the loop, FK_DTI/FK_DTI.py:115) on the device: tensors = n C-order 3x3 float64 tensors
+ * (host), rgb = n x 3 float64 (host): the tensor diagonal divided by its mean over the brain voxels (max of the diagonal
+ * > 0), clipped to [0, 10], x**exponent + linear*x, normalised and clipped again.  Same arithmetic as the reference except
+ * for the summation order of the two means (deterministic here, pairwise in numpy): agreement ~1e-15 relative. */
+int tgtk_dti_rgb_host(int device, const double *tensors, int64_t n, double exponent, double linear, double *rgb);
+
 /* Batched 3x3 symmetric eigen-elongation on the device: tensors = n C-order 3x3 float64 tensors (host),
  * out = n 3x3 float32 tensors (host), the dtype the reference returns.  Replaces
  * tools.elongate_tensor_along_main_axis_torch (TumorGrowthToolkit/FK_DTI/tools.py:109-164; called from

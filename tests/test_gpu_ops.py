@@ -322,3 +322,16 @@ def test_slab_single_rank_equals_plain_loop(L):
     got = slab.fk2c_loop(*a2, halo=2, driver="p2p")
     for k in "PNS":
         assert np.array_equal(got["state"][k], ref["state"][k]), k
+
+
+@pytest.mark.parametrize("key,exponent,linear", [("dti_rgb_exp1", 1, 0), ("dti_rgb_exp15", 1.5, 0.2)])
+def test_rgb_from_tensor_kernels_match_reference(L, gold_solve, key, exponent, linear):
+    """tools.makeXYZ_rgb_from_tensor on the device (tgtk_dti_rgb_host) against the reference's own output
+    (tests/golden/solve.npz: dti_rgb_*): only the summation order of the two brain means differs."""
+    from tumorgrowthtoolkit_b200 import synthetic, _ops
+    T = synthetic.dti_tensor_field(gold_solve["wm"], gold_solve["gm"], seed=7)
+    got = _ops.dti_rgb(T, exponent, linear)
+    want = gold_solve[key]
+    assert got.shape == want.shape
+    assert _maxerr(got, want) <= 1e-12
+    assert np.array_equal(got == 0, want == 0)

@@ -34,6 +34,8 @@ def cpu_loops(monkeypatch, oracle):
         return oracle.zoom_linear(a, out_shape)
     from tumorgrowthtoolkit_b200 import _host
     monkeypatch.setattr(_host, "_device_resample", cpu_resample)
+    from tumorgrowthtoolkit_b200.FK_DTI import tools
+    monkeypatch.setattr(tools, "makeXYZ_rgb_from_tensor_cuda", lambda t, exponent=1, linear=0, device=0: tools.makeXYZ_rgb_from_tensor(t, exponent, linear))
 
 
 @pytest.mark.parametrize("name", sorted(FK_CASES))

@@ -64,7 +64,7 @@ class FK_DTI_Solver(FK_Solver):
                 tensors = tools.elongate_tensor_along_main_axis_torch(tensors, scaling)
             else:
                 raise ValueError(f"elongation_backend must be 'torch' or 'cuda', got {backend!r}")
-        rgb = tools.makeXYZ_rgb_from_tensor(tensors, exponent=exponent, linear=linear)
+        rgb = tools.makeXYZ_rgb_from_tensor_cuda(tensors, exponent=exponent, linear=linear, device=self._device())
         full_tensor = bool(p.get('dti_full_tensor', False))
         if full_tensor and (exponent != 1 or linear != 0):
             raise ValueError("dti_full_tensor needs diffusionTensorExponent=1 and diffusionTensorLinear=0")

@@ -71,6 +71,14 @@ def makeXYZ_rgb_from_tensor(tensor, exponent=1, linear=0):
     return normalise(out)
 
 
+def makeXYZ_rgb_from_tensor_cuda(tensor, exponent=1, linear=0, device=0):
+    """`makeXYZ_rgb_from_tensor` as device kernels (csrc: rgb_extract / rgb_mean / rgb_normalise): what FK_DTI_Solver.solve
+    runs on the whole input volume before the loop.  Differs from the numpy function above only in the summation order
+    of the two brain means (~1e-15 relative)."""
+    from .. import _ops
+    return _ops.dti_rgb(tensor, exponent, linear, device=device)
+
+
 def offdiagonal_from_tensor(tensor):
     """(X,Y,Z,3) array [D_xy, D_xz, D_yz] in the units of makeXYZ_rgb_from_tensor(tensor, 1, 0):
     the same two brain-mean normalisations, no clipping (|D_ab| <= sqrt(D_aa D_bb) anyway).

@@ -29,6 +29,8 @@ def resample_linear(a, factor, device=0):
     if a.dtype != np.float64:
         return _ndimage_zoom(a, factor, order=1)
     out_shape = _out_shape(a.shape, factor)
+    if out_shape == a.shape:
+        return a                    # zoom(x, 1.0, order=1) is the exact identity; nothing downstream writes to it
     if a.ndim == 3:
         return _device_resample(a, out_shape, device=device)
     assert a.ndim == 4 and out_shape[3] == a.shape[3], "4-D arrays are resampled per channel"

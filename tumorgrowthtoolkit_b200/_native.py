@@ -112,6 +112,7 @@ def lib():
                                   c_dbl, c_dbl, c_dbl, c_dbl, c_int, c_int, vp, vp, vp]
     L.tgtk_resample_linear_host.argtypes = [c_int, vp, _I64x3, i3, i3, i3, vp, i3]
     L.tgtk_elongate_tensors_host.argtypes = [c_int, vp, ctypes.c_int64, c_dbl, vp]
+    L.tgtk_dti_rgb_host.argtypes = [c_int, vp, ctypes.c_int64, c_dbl, c_dbl, vp]
     if L.tgtk_abi_version() != 1:
         raise NativeError("libtgtk_b200.so ABI version mismatch")
     _lib = L

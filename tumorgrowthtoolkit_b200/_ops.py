@@ -143,3 +143,15 @@ def elongate_tensors(tensors, scale_factor, device=0):
     n = int(np.prod(t.shape[:-2], dtype=np.int64))
     nat._check(L.tgtk_elongate_tensors_host(int(device), t.ctypes.data, n, float(scale_factor), out.ctypes.data))
     return out
+
+
+def dti_rgb(tensors, exponent=1, linear=0, device=0):
+    """tools.makeXYZ_rgb_from_tensor (TumorGrowthToolkit/FK_DTI/tools.py:166-187) on the GPU: (X,Y,Z,3,3) tensors ->
+    (X,Y,Z,3) float64 per-axis diffusivity weights (brain-mean 1, clipped to [0, 10], x**exponent + linear*x, renormalised)."""
+    L = nat.lib()
+    t = np.ascontiguousarray(tensors, dtype=np.float64)
+    assert t.ndim == 5 and t.shape[-2:] == (3, 3), "tensors must have shape (X, Y, Z, 3, 3)"
+    out = np.empty(t.shape[:3] + (3,), dtype=np.float64)
+    nat._check(L.tgtk_dti_rgb_host(int(device), t.ctypes.data, int(np.prod(t.shape[:3], dtype=np.int64)), float(exponent), float(linear),
+                                   out.ctypes.data))
+    return out

@@ -1836,6 +1836,135 @@ int tgtk_sim_segmentation_async(tgtk_sim *s, const int32_t lo[3], const int32_t 
     return 0;
 }
 
+// ---- tools.makeXYZ_rgb_from_tensor (FK_DTI/tools.py:166-187) on the device ------------------------------------------
+namespace {
+// pass 1: diagonal of every 3x3 tensor -> rgb, brain mask (max of the diagonal > 0, tools.py:172), per-block sum and
+// count of the entries of brain voxels
+__global__ void __launch_bounds__(256) rgb_extract_kernel(const double *__restrict__ t, double *__restrict__ rgb,
+                                                          unsigned char *__restrict__ brain, int64_t n, double *__restrict__ psum,
+                                                          unsigned long long *__restrict__ pcnt)
+{
+    __shared__ double rs[8];
+    __shared__ unsigned long long rc[8];
+    double s = 0.0;
+    unsigned long long c = 0;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        const double a = t[q * 9], b = t[q * 9 + 4], d = t[q * 9 + 8];
+        rgb[q * 3] = a; rgb[q * 3 + 1] = b; rgb[q * 3 + 2] = d;
+        const bool in = fmax(fmax(a, b), d) > 0.0;
+        brain[q] = in;
+        if (in) { s += (a + b) + d; c += 3; }
+    }
+    s = warp_sum(s);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) { rs[threadIdx.x >> 5] = s; rc[threadIdx.x >> 5] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0; unsigned long long b = 0;
+        for (int w = 0; w < 8; ++w) { a += rs[w]; b += rc[w]; }
+        psum[blockIdx.x] = a; pcnt[blockIdx.x] = b;
+    }
+}
+
+// one block, fixed order: stat[which] = sum(psum) / count; the count is summed from pcnt (pass 1) or reused (pass 2)
+__global__ void __launch_bounds__(256) rgb_mean_kernel(const double *psum, const unsigned long long *pcnt, int nparts, double *stat,
+                                                       unsigned long long *count, int which)
+{
+    __shared__ double rs[256];
+    __shared__ unsigned long long rc[256];
+    double a = 0.0; unsigned long long b = 0;
+    for (int i = threadIdx.x; i < nparts; i += 256) { a += psum[i]; if (pcnt) b += pcnt[i]; }
+    rs[threadIdx.x] = a; rc[threadIdx.x] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ta = 0.0; unsigned long long tb = 0;
+        for (int i = 0; i < 256; ++i) { ta += rs[i]; tb += rc[i]; }
+        if (pcnt) *count = tb;
+        stat[which] = ta / (double)(*count);
+    }
+}
+
+// x /= mean; x[x > 10] = 10; x[x < 0] = 0 (tools.py:174-178).  stage 0 then applies x**exponent + x*linear (:183) and
+// sums the result over the brain voxels for the second normalisation (:185)
+__global__ void __launch_bounds__(256) rgb_normalise_kernel(double *__restrict__ rgb, const unsigned char *__restrict__ brain, int64_t n,
+                                                            const double *__restrict__ stat, int stage, double exponent, double linear,
+                                                            double *__restrict__ psum)
+{
+    __shared__ double rs[8];
+    const double m = stat[stage];
+    double s = 0.0;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        double v[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            double x = rgb[q * 3 + a] / m;
+            x = (x > 10.0) ? 10.0 : x;
+            x = (x < 0.0) ? 0.0 : x;
+            if (stage == 0) x = ((exponent == 1.0) ? x : pow(x, exponent)) + x * linear;
+            v[a] = x;
+            rgb[q * 3 + a] = x;
+        }
+        if (stage == 0 && brain[q]) s += (v[0] + v[1]) + v[2];
+    }
+    if (stage == 0) {
+        s = warp_sum(s);
+        if ((threadIdx.x & 31) == 0) rs[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) { double a = 0.0; for (int w = 0; w < 8; ++w) a += rs[w]; psum[blockIdx.x] = a; }
+    }
+}
+}  // namespace
+
+int tgtk_dti_rgb_host(int device, const double *tensors, int64_t n, double exponent, double linear, double *rgb)
+{
+    if (!tensors || !rgb) return fail("tgtk_dti_rgb_host", "null argument");
+    if (n < 1) return fail("tgtk_dti_rgb_host", "empty tensor volume");
+    CU(cudaSetDevice(device));
+    cudaStream_t st = nullptr;
+    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    // the tensor volume (72 bytes per voxel, 643 MB for 240x240x155) goes through in slabs
+    const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 21);
+    const int nslab = (int)((n + chunk - 1) / chunk), per = grid_1d((size_t)chunk), nb = grid_1d((size_t)n);
+    const int nparts = std::max(per * nslab, nb);
+    double *dt = nullptr, *drgb = nullptr, *dsum = nullptr, *dstat = nullptr;
+    unsigned long long *dcnt = nullptr;
+    unsigned char *dbrain = nullptr;
+    int rc = 0;
+    cudaError_t e = cudaMallocAsync((void **)&drgb, (size_t)n * 24, st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&dbrain, (size_t)n, st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&dt, (size_t)chunk * 72, st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&dsum, sizeof(double) * nparts, st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&dcnt, sizeof(unsigned long long) * (nparts + 1), st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&dstat, sizeof(double) * 2, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dsum, 0, sizeof(double) * nparts, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dcnt, 0, sizeof(unsigned long long) * (nparts + 1), st);
+    for (int k = 0; k < nslab && e == cudaSuccess; ++k) {
+        const int64_t q = (int64_t)k * chunk, m = std::min(chunk, n - q);
+        e = cudaMemcpyAsync(dt, tensors + q * 9, (size_t)m * 72, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) {
+            rgb_extract_kernel<<<grid_1d((size_t)m), 256, 0, st>>>(dt, drgb + q * 3, dbrain + q, m, dsum + (size_t)k * per, dcnt + (size_t)k * per);
+            e = cudaGetLastError();
+        }
+    }
+    unsigned long long *dcount = dcnt + nparts;
+    if (e == cudaSuccess) { rgb_mean_kernel<<<1, 256, 0, st>>>(dsum, dcnt, per * nslab, dstat, dcount, 0); e = cudaGetLastError(); }
+    if (e == cudaSuccess) { rgb_normalise_kernel<<<nb, 256, 0, st>>>(drgb, dbrain, n, dstat, 0, exponent, linear, dsum); e = cudaGetLastError(); }
+    if (e == cudaSuccess) { rgb_mean_kernel<<<1, 256, 0, st>>>(dsum, nullptr, nb, dstat, dcount, 1); e = cudaGetLastError(); }
+    if (e == cudaSuccess) { rgb_normalise_kernel<<<nb, 256, 0, st>>>(drgb, dbrain, n, dstat, 1, exponent, linear, dsum); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rgb, drgb, (size_t)n * 24, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail("tgtk_dti_rgb_host", cudaGetErrorString(e));
+    if (dt) cudaFreeAsync(dt, st);
+    if (drgb) cudaFreeAsync(drgb, st);
+    if (dbrain) cudaFreeAsync(dbrain, st);
+    if (dsum) cudaFreeAsync(dsum, st);
+    if (dcnt) cudaFreeAsync(dcnt, st);
+    if (dstat) cudaFreeAsync(dstat, st);
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    return rc;
+}
+
 // ---- batched restore + zoom of snapshots / the final state into pageable host memory ------------------------------
 namespace {
 struct PinnedRing {            // page-locked staging buffers, kept for the life of the process (page-locking 71 MB costs ~25 ms)
