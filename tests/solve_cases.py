@@ -133,7 +133,9 @@ def atlas_dti_params(labels, gold, case):
 def compare_atlas_dti(case, res, gold, tol):
     assert res["success"], res.get("error")
     assert str(res["stopping_criteria"]) == str(gold[case + "/stopping_criteria"])
-    assert float(res["final_time"]) == float(gold[case + "/final_time"])        # same stop step, same dt
+    # same stop step; dt = T / Nt carries the ~1e-16 relative difference of max(rgb) (device vs numpy summation order of the brain means)
+    ft = float(gold[case + "/final_time"])
+    assert abs(float(res["final_time"]) - ft) <= 1e-12 * max(1.0, ft), (res["final_time"], ft)
     fv = float(gold[case + "/final_volume"])
     assert abs(float(res["final_volume"]) - fv) <= max(tol, 1e-9) * fv
     fs = res["final_state"]
