@@ -357,6 +357,29 @@ def gen_dti_atlas():
     print("atlas_dti_res05.npz", os.path.getsize(os.path.join(GOLD, "atlas_dti_res05.npz")))
 
 
+def gen_segmap():
+    """create_segmentation_map of the unmodified reference script (synthetic_gens/generatePatient_FK_2c.py:67-83) on seeded
+    fields, three threshold sets drawn with the script's own law: pins the label map the ensemble path produces."""
+    import importlib.util
+    import_reference()                                   # also mocks nibabel for the script's imports
+    spec = importlib.util.spec_from_file_location("ref_generate_patient", os.path.join(REF, "synthetic_gens", "generatePatient_FK_2c.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(20261021)
+    shape = (24, 20, 18)
+    P = rng.uniform(0, 1, shape) * (rng.uniform(0, 1, shape) < 0.7)
+    N = rng.uniform(0, 0.5, shape) * (rng.uniform(0, 1, shape) < 0.4)
+    P[0, 0, :6] = [0.15, 0.4, 0.12, 0.2, 0.25, 0.6]      # values exactly on thresholds
+    N[0, 1, :3] = [0.12, 0.05, 0.2]
+    out = {"P": P, "N": N}
+    ths = [(0.12, 0.4, 0.15), (0.05, 0.25, 0.12), (0.2, 0.6, 0.2)]
+    out["thresholds"] = np.array(ths)
+    for i, th in enumerate(ths):
+        out[f"seg{i}"] = mod.create_segmentation_map(P, N, *th)
+    np.savez_compressed(os.path.join(GOLD, "segmap.npz"), **out)
+    print("segmap.npz", os.path.getsize(os.path.join(GOLD, "segmap.npz")))
+
+
 def elongate_inputs():
     """Seeded (6,7,5,3,3) tensor field for the elongation (tools.py:109-164): SPD tensors with separated
     eigenvalues, isotropic and axis-aligned degenerate tensors, zeros (background)."""
@@ -387,6 +410,7 @@ def gen_elongate():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    groups = sys.argv[1:] or ["ops", "solve", "atlas", "elongate", "dti_atlas"]
+    groups = sys.argv[1:] or ["ops", "solve", "atlas", "elongate", "dti_atlas", "segmap"]
     for g in groups:
-        {"ops": gen_ops, "solve": gen_solve, "atlas": gen_atlas, "elongate": gen_elongate, "dti_atlas": gen_dti_atlas}[g]()
+        {"ops": gen_ops, "solve": gen_solve, "atlas": gen_atlas, "elongate": gen_elongate, "dti_atlas": gen_dti_atlas,
+         "segmap": gen_segmap}[g]()

@@ -19,3 +19,16 @@ def test_shard_partitions_and_balances():
     assert sorted(i for part in parts for i in part) == list(range(64))
     loads = [sum(ensemble.step_count(params[i])[0] for i in part) for part in parts]
     assert max(loads) <= 1.15 * min(loads)
+
+
+def test_segmentation_map_matches_reference_script():
+    """ensemble.create_segmentation_map against labels produced by the reference script's own function
+    (tests/make_golden.py:gen_segmap imports synthetic_gens/generatePatient_FK_2c.py:67-83), values on the thresholds included.
+    tests/test_gpu_ensemble.py holds the device label kernel to this host function on every patient."""
+    import os
+    from tumorgrowthtoolkit_b200 import ensemble
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "segmap.npz"))
+    for i, th in enumerate(g["thresholds"]):
+        got = ensemble.create_segmentation_map(g["P"], g["N"], *th)
+        assert np.array_equal(got, g[f"seg{i}"])
+        assert set(np.unique(got)) <= {0, 1, 3, 4}

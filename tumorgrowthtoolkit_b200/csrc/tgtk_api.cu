@@ -117,6 +117,7 @@ struct tgtk_sim {
     unsigned partials_cap = 0;
     // temporal blocking (tgtk_kernels_tb.cuh): two steps per launch where a kernel exists (FK, FK_DTI) and the
     // run is host-scheduled or speculative.  TGTK_TB: 1 on, 0 off, -1 auto (fp64 boxes of more than twice the L2)
+    int zigzag = 1;        // serpentine sweep of the two-voxel kernels (TGTK_ZIGZAG)
     int tb = -1;
     int tb_rows = 18;      // thread rows of the two-step kernel's block: 18 (16 output rows, 576 threads) or 10 (8, 320)
     dim3 tb_grid, tb_block;
@@ -347,6 +348,7 @@ template <typename T> static void fill_args(const tgtk_sim *s, StepArgs<T> &a)
     a.l2pf = effective_l2pf(s);
     a.x_lo = 0;
     a.x_hi = p.X;
+    a.zigzag = s->zigzag;
     a.slab = 0;
     if (s->slab_on) {
         a.slab = 1;
@@ -1225,6 +1227,7 @@ int tgtk_sim_create_ex(tgtk_sim **out, const tgtk_params *params, int device, vo
     if (const char *v = getenv("TGTK_L2PF")) s->l2pf = atoi(v);
     if (const char *v = getenv("TGTK_PDL")) s->pdl = atoi(v);
     if (const char *v = getenv("TGTK_TB")) s->tb = atoi(v);
+    if (const char *v = getenv("TGTK_ZIGZAG")) s->zigzag = atoi(v) != 0;
     if (const char *v = getenv("TGTK_TB_ROWS")) s->tb_rows = atoi(v);
     if (const char *v = getenv("TGTK_TMA_ROWS")) s->tma_rows = (atoi(v) == 8) ? 8 : 4;
     if (const char *v = getenv("TGTK_TMA_STAGES")) s->tma_stages = (atoi(v) == 2) ? 2 : (atoi(v) == 4) ? 4 : 3;

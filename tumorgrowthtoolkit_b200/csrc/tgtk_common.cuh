@@ -62,6 +62,7 @@ template <typename T> struct StepArgs {
     int l2pf;
     // planes [x_lo, x_hi) of axis 0 are computed by this launch (two-voxel kernels; default: the whole box)
     int x_lo, x_hi;
+    int zigzag;               // two-voxel kernels: odd steps march axis 0 downwards (L2 reuse of what the previous step wrote last)
     // Fused slab mode (tgtk_nccl.inc, one rank per GPU, axis 0 decomposed, one ghost plane per side): the blocks
     // that compute the rank's lowest / highest owned plane ALSO store it into the neighbouring rank's ghost plane
     // (peer-mapped memory, NVLink).  A launch's stores are visible system-wide when the launch has completed, so

@@ -322,9 +322,7 @@ __device__ __forceinline__ Stage2 stage2_setup(const StepArgs<T> &a, int lx)
 }
 
 // Marching direction of a block: up (x0 -> x1-1) or down.  The face fluxes are antisymmetric and the sums
-// commutative, so a voxel's result does not depend on the direction (bitwise).  Downward marching is not used at
-// present: it was written to get a slab's upper boundary plane out early, which the kernel-boundary publication
-// of the fused slab driver made unnecessary.
+// commutative, so a voxel's result does not depend on the direction (bitwise).
 struct March2 {
     bool down;
     int xs, dx, n;            // first plane, +-1, number of planes
@@ -333,25 +331,28 @@ struct March2 {
     uint32_t wrapd;
 };
 
-template <typename T> __device__ __forceinline__ March2 march2_setup(const StepArgs<T> &a, Stage2 &g)
+template <typename T> __device__ __forceinline__ March2 march2_setup(const StepArgs<T> &a, Stage2 &g, int par)
 {
     March2 m;
-    m.down = false;           // (kept for experiments: with kernel-boundary publication the push time inside a step is irrelevant)
+    // serpentine sweep: odd steps march downwards, so a step starts on the planes the previous step wrote last --
+    // the part of the state that is still in L2 (the ping-pong parity is the step's parity)
+    m.down = a.zigzag && (par & 1);
     m.n = g.x1 - g.x0;
     m.xs = g.x0;
     m.dx = 1;
     m.dsx = g.sx;
-    m.wrapx = a.X;
+    m.wrapx = a.X;            // upwards: the plane after X-1 is plane 0
     m.wrapd = 0u - g.wrap_back;
-    if (m.down) {             // start at the segment's top plane; "previous" is the plane above (never wraps: ghosts exist)
+    if (m.down) {             // start at the segment's top plane; "previous" is the plane above it, the plane after 0 is X-1
         const uint32_t up = (uint32_t)(m.n - 1) * g.sx;
         g.c0 += up; g.c1 += up; g.h += up;
-        g.prev0 = g.c0 + g.sx; g.prev1 = g.c1 + g.sx;
+        const uint32_t behind = (g.x1 == a.X) ? 0u - g.wrap_back : g.sx;
+        g.prev0 = g.c0 + behind; g.prev1 = g.c1 + behind;
         m.xs = g.x1 - 1;
         m.dx = -1;
         m.dsx = 0u - g.sx;
-        m.wrapx = -2;
-        m.wrapd = m.dsx;
+        m.wrapx = 1;          // (x + 1 == wrapx) <=> x == 0
+        m.wrapd = g.wrap_back;
     }
     return m;
 }
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> 
     const T *__restrict__ kc = a.coef[0];
     const T *__restrict__ bc = a.coef[1];
     Stage2 g = stage2_setup<T, TZ, TYT, RS>(a, lx);
-    const March2 mm = march2_setup(a, g);
+    const March2 mm = march2_setup(a, g, sc.par);
     const T closed = -Big<T>::v;
     auto keff = [&](T pq, T nq, T kq) { return (pq + nq <= a.th_necro) ? kq : closed; };
     auto load = [&](Vox2c<T> &v, uint32_t off) { v.p = P[off]; v.n = N[off]; v.s = S[off]; v.b = bc[off]; v.k = kc[off]; };
@@ -496,7 +497,7 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk_step_v4(const StepArgs<T> a,
     T *__restrict__ out = a.buf[sc.par ^ 1][0];
     const T *__restrict__ kc = a.coef[0];
     Stage2 g = stage2_setup<T, TZ, TYT, RS>(a, lx);
-    const March2 mm = march2_setup(a, g);
+    const March2 mm = march2_setup(a, g, sc.par);
     double s = 0.0;
     griddep_launch();
     griddep_wait();
@@ -579,7 +580,7 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) dti_step_v4(const StepArgs<T> a
     const T *__restrict__ dya = a.coef[1];
     const T *__restrict__ dza = a.coef[2];
     Stage2 g = stage2_setup<T, TZ, TYT, RS>(a, lx);
-    const March2 mm = march2_setup(a, g);
+    const March2 mm = march2_setup(a, g, sc.par);
     double s = 0.0;
     auto load = [&](VoxDti<T> &v, uint32_t off) { v.u = u[off]; v.d0 = dxa[off]; v.d1 = dya[off]; v.d2 = dza[off]; };
 
