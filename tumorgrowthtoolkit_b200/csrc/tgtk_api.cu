@@ -117,7 +117,7 @@ struct tgtk_sim {
     unsigned partials_cap = 0;
     // temporal blocking (tgtk_kernels_tb.cuh): two steps per launch where a kernel exists (FK, FK_DTI) and the
     // run is host-scheduled or speculative.  TGTK_TB: 1 on, 0 off, -1 auto (fp64 boxes of more than twice the L2)
-    int zigzag = 1;        // serpentine sweep of the two-voxel kernels (TGTK_ZIGZAG)
+    int zigzag = 0;        // serpentine sweep of the two-voxel kernels (TGTK_ZIGZAG=1): measured +-1 %, off by default
     int tb = -1;
     int tb_rows = 18;      // thread rows of the two-step kernel's block: 18 (16 output rows, 576 threads) or 10 (8, 320)
     dim3 tb_grid, tb_block;

@@ -88,11 +88,23 @@ __device__ __forceinline__ double fast_exp(double x)
     const double nf = t - magic;
     double r = fma(nf, -6.93147180369123816490e-01, x);           // ln2 high part
     r = fma(nf, -1.90821492927058770002e-10, r);                  // ln2 low part
+#ifndef TGTK_EXP_ESTRIN
     double p = kExpTaylor[0];
 #pragma unroll
     for (int i = 1; i < 11; ++i) p = fma(p, r, kExpTaylor[i]);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
+#else
+    // Estrin's scheme: the same degree-12 polynomial, dependency depth 4 instead of 13 (the kernel that calls this
+    // is bound by fp64 latency chains, not by the two extra multiplications); c_i = 1/i! = kExpTaylor[12 - i]
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double a0 = fma(r, 1.0, 1.0), a1 = fma(kExpTaylor[9], r, kExpTaylor[10]), a2 = fma(kExpTaylor[7], r, kExpTaylor[8]);
+    const double a3 = fma(kExpTaylor[5], r, kExpTaylor[6]), a4 = fma(kExpTaylor[3], r, kExpTaylor[4]);
+    const double a5 = fma(kExpTaylor[1], r, kExpTaylor[2]);
+    const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
+    const double d0 = fma(b1, r4, b0), d1 = fma(kExpTaylor[0], r4, b2);
+    const double p = fma(d1, r8, d0);
+#endif
     return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 __device__ __forceinline__ float fast_exp(float x) { return expf(x); }
