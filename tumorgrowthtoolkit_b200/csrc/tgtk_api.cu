@@ -75,6 +75,7 @@ struct tgtk_sim {
     int v4_threads = 128;  // fk2c_step_v4 block size: 128 (32x4 threads, 32x8 voxels) or 256 (32x8 threads, 32x16 voxels)
     int pf = 1;            // FK_2c staged kernel: prefetch distance in planes (1: two register sets, 4 blocks/SM; 2: three sets)
     int force_tz = 0;      // 0: pick the tile width by lane waste
+    int force_lx = 0;      // 0: planes per segment from the wave model (configure_launch)
     int l2pf = -1;         // v4 kernels: L2 prefetch distance in planes (TGTK_L2PF); 0 = off, -1 = auto:
                            // 2 planes when the arrays a step touches do not fit in L2, else off (measured:
                            // the requests only cost time when the working set is L2 resident)
@@ -572,7 +573,8 @@ template <typename T> static cudaError_t launch_step(tgtk_sim *s)
             if (mb >= 3) return launch_v4(s, fk2c_step_v4<T, 16, 8, 6>, a, s->lx);
             else return launch_v4(s, fk2c_step_v4<T, 16, 8, 4>, a, s->lx);
         } else if (s->block.y == 4) {
-            if (mb == 5) return launch_v4(s, fk2c_step_v4<T, 32, 4, 5>, a, s->lx);
+            if (mb == 5) return launch_v4(s, fk2c_step_v4<T, 32, 4, 5, 1>, a, s->lx);
+            if (mb == 14) return launch_v4(s, fk2c_step_v4<T, 32, 4, 4, 1>, a, s->lx);
             if (mb >= 3) return launch_v4(s, fk2c_step_v4<T, 32, 4, 6>, a, s->lx);
             else return launch_v4(s, fk2c_step_v4<T, 32, 4, 4>, a, s->lx);
         } else {
@@ -699,7 +701,8 @@ static const void *v4_kernel(int model, int dtype, int rows, int minb)
         return rows == 4 ? (const void *)dti_step_v4<float, 32, 4, 8> : (const void *)dti_step_v4<float, 32, 8, 4>;
     }
     if (minb == 0) minb = (dtype == TGTK_F64) ? 2 : 3;   // fp64: 120 registers, fp32: 76 (measured faster)
-    if (rows == 4 && minb == 5) return dtype == TGTK_F64 ? (const void *)fk2c_step_v4<double, 32, 4, 5> : (const void *)fk2c_step_v4<float, 32, 4, 5>;
+    if (rows == 4 && minb == 5) return dtype == TGTK_F64 ? (const void *)fk2c_step_v4<double, 32, 4, 5, 1> : (const void *)fk2c_step_v4<float, 32, 4, 5, 1>;
+    if (rows == 4 && minb == 14) return dtype == TGTK_F64 ? (const void *)fk2c_step_v4<double, 32, 4, 4, 1> : (const void *)fk2c_step_v4<float, 32, 4, 4, 1>;
     if (dtype == TGTK_F64) {
         if (rows == 4) return minb >= 3 ? (const void *)fk2c_step_v4<double, 32, 4, 6> : (const void *)fk2c_step_v4<double, 32, 4, 4>;
         return minb >= 3 ? (const void *)fk2c_step_v4<double, 32, 8, 3> : (const void *)fk2c_step_v4<double, 32, 8, 2>;
@@ -789,6 +792,7 @@ static int configure_launch(tgtk_sim *s)
             const double eff = waves / std::ceil(waves) * (lx / (lx + 0.6)) * ((double)NX / ((double)ns * lx));
             if (eff > best_eff + 1e-9) { best_eff = eff; best_lx = lx; }
         }
+        if (s->force_lx > 0) best_lx = std::min(s->force_lx, NX);      // TGTK_LX: experiments
         s->lx = best_lx;
         const int nseg = (NX + s->lx - 1) / s->lx;
         s->block = dim3((four || zp1) ? 16 : tz, two_rows ? v4rows : ty, 1);
@@ -1224,6 +1228,7 @@ int tgtk_sim_create_ex(tgtk_sim **out, const tgtk_params *params, int device, vo
     if (const char *v = getenv("TGTK_NARROW_PENALTY")) s->narrow_penalty = atof(v);
     if (const char *v = getenv("TGTK_GRAPH")) s->use_graph = atoi(v) != 0;
     if (const char *v = getenv("TGTK_TZ")) s->force_tz = atoi(v);
+    if (const char *v = getenv("TGTK_LX")) s->force_lx = atoi(v);
     if (const char *v = getenv("TGTK_L2PF")) s->l2pf = atoi(v);
     if (const char *v = getenv("TGTK_PDL")) s->pdl = atoi(v);
     if (const char *v = getenv("TGTK_TB")) s->tb = atoi(v);

@@ -359,7 +359,10 @@ template <typename T> __device__ __forceinline__ March2 march2_setup(const StepA
 
 template <typename T> struct Vox2c { T p, n, s, b, k; };
 
-template <typename T, int TZ, int TYT, int MINB = 2>
+// LL = 1 ("late loads"): the own-column values of the next plane are requested AFTER the barrier instead of at the top
+// of the step -- their registers are then not live across the in-plane section, which is what lets the kernel fit
+// 5 blocks per SM (96 registers) without spilling; the bulk L2 prefetch keeps the shortened distance cheap.
+template <typename T, int TZ, int TYT, int MINB = 2, int LL = 0>
 __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> a, const int lx)
 {
     constexpr int TYV = 2 * TYT, RS = TZ + 2, PL = (TYV + 2) * RS;
@@ -418,8 +421,10 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> 
         // request the next plane of the march: both own voxels and the ring
         const uint32_t adv = (x + 1 == mm.wrapx) ? mm.wrapd : mm.dsx;
         const uint32_t n0 = g.c0 + adv, n1 = g.c1 + adv;
-        load(p0, n0);
-        load(p1, n1);
+        if (!LL) {
+            load(p0, n0);
+            load(p1, n1);
+        }
         g.h += adv;
         if (g.ring) { hp = P[g.h]; hn = N[g.h]; hk = kc[g.h]; hsv = S[g.h]; hb = bc[g.h]; }
         if (pf.on) {                           // this tile strip of plane x + l2pf into L2
@@ -444,6 +449,10 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> 
         T sp1 = a.hy * (fp_mid - relu2(c1.k + pd.b) * (c1.p - pd.a));
         T ss0 = a.gy * (relu2(su.b + c0.b) * (su.a - c0.s) - fs_mid);
         T ss1 = a.gy * (fs_mid - relu2(c1.b + sd.b) * (c1.s - sd.a));
+        if (LL) {
+            load(p0, n0);
+            load(p1, n1);
+        }
         sp0 += a.hz * (relu2(pl0.b + c0.k) * (pl0.a - c0.p) - relu2(c0.k + pr0.b) * (c0.p - pr0.a));
         sp1 += a.hz * (relu2(pl1.b + c1.k) * (pl1.a - c1.p) - relu2(c1.k + pr1.b) * (c1.p - pr1.a));
         ss0 += a.gz * (relu2(sl0.b + c0.b) * (sl0.a - c0.s) - relu2(c0.b + sr0.b) * (c0.s - sr0.a));

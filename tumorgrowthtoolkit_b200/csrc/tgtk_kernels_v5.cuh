@@ -78,6 +78,13 @@ __device__ __forceinline__ float2 heaviside50_pair(float2 s, float sigma)
     return fma2(r, bc2(-1.0f), bc2(1.0f));
 }
 
+// Left / right neighbours of a z pair: the voxel left of my a-element is the b-element of the lane below, the voxel
+// right of my b-element the a-element of the lane above -- one SHFL each instead of a scalar shared-memory read at a
+// 16-byte lane stride (4-way bank conflict, what made round 1's z-pair FK / FK_2c kernels lose to the two-voxel ones).
+// Only the first / last lane of a tile row (TZL lanes; a warp holds 32 / TZL rows) reads the ring slot beside the tile.
+template <int TZL> __device__ __forceinline__ float from_left(float mine_b) { return __shfl_up_sync(0xffffffffu, mine_b, 1, TZL); }
+template <int TZL> __device__ __forceinline__ float from_right(float mine_a) { return __shfl_down_sync(0xffffffffu, mine_a, 1, TZL); }
+
 // ---- geometry -------------------------------------------------------------------------------------
 struct Stage4 {
     int x0, x1;
@@ -226,12 +233,18 @@ __global__ void __launch_bounds__(TZL *TYT, MINB) fk2c_step_v5(const StepArgs<fl
         __syncthreads();
         const float4 pu = t0[o0 - RS], pd = t0[o1 + RS];       // rows y-1 and y+2: (P_a, P_b, k_a, k_b)
         const float4 su = t1[o0 - RS], sd = t1[o1 + RS];       // (S_a, S_b, b_a, b_b)
-        const float *f0 = reinterpret_cast<const float *>(t0), *f1 = reinterpret_cast<const float *>(t1);
-        const int l0 = (o0 - 1) * 4 + 1, r0 = (o0 + 1) * 4, l1 = (o1 - 1) * 4 + 1, r1 = (o1 + 1) * 4;
-        const float pl0 = f0[l0], kl0 = f0[l0 + 2], pr0 = f0[r0], kr0 = f0[r0 + 2];
-        const float pl1 = f0[l1], kl1 = f0[l1 + 2], pr1 = f0[r1], kr1 = f0[r1 + 2];
-        const float sl0 = f1[l0], bl0 = f1[l0 + 2], sr0 = f1[r0], br0 = f1[r0 + 2];
-        const float sl1 = f1[l1], bl1 = f1[l1 + 2], sr1 = f1[r1], br1 = f1[r1 + 2];
+        float pl0 = from_left<TZL>(c0.p.y), kl0 = from_left<TZL>(c0.k.y), sl0 = from_left<TZL>(c0.s.y), bl0 = from_left<TZL>(c0.b.y);
+        float pr0 = from_right<TZL>(c0.p.x), kr0 = from_right<TZL>(c0.k.x), sr0 = from_right<TZL>(c0.s.x), br0 = from_right<TZL>(c0.b.x);
+        float pl1 = from_left<TZL>(c1.p.y), kl1 = from_left<TZL>(c1.k.y), sl1 = from_left<TZL>(c1.s.y), bl1 = from_left<TZL>(c1.b.y);
+        float pr1 = from_right<TZL>(c1.p.x), kr1 = from_right<TZL>(c1.k.x), sr1 = from_right<TZL>(c1.s.x), br1 = from_right<TZL>(c1.b.x);
+        if (threadIdx.x == 0) {
+            const float4 e0 = t0[o0 - 1], e1 = t1[o0 - 1], e2 = t0[o1 - 1], e3 = t1[o1 - 1];
+            pl0 = e0.y; kl0 = e0.w; sl0 = e1.y; bl0 = e1.w; pl1 = e2.y; kl1 = e2.w; sl1 = e3.y; bl1 = e3.w;
+        }
+        if (threadIdx.x == TZL - 1) {
+            const float4 e0 = t0[o0 + 1], e1 = t1[o0 + 1], e2 = t0[o1 + 1], e3 = t1[o1 + 1];
+            pr0 = e0.x; kr0 = e0.z; sr0 = e1.x; br0 = e1.z; pr1 = e2.x; kr1 = e2.z; sr1 = e3.x; br1 = e3.z;
+        }
         // y
         float2 sp0 = mul2(cy2, sub2(mul2(relu2(add2(make_float2(pu.z, pu.w), c0.k)), sub2(make_float2(pu.x, pu.y), c0.p)), fp_mid));
         float2 sp1 = mul2(cy2, sub2(fp_mid, mul2(relu2(add2(c1.k, make_float2(pd.z, pd.w))), sub2(c1.p, make_float2(pd.x, pd.y)))));
@@ -339,10 +352,10 @@ __global__ void __launch_bounds__(TZL *TYT, MINB) fk_step_v5(const StepArgs<floa
         const float g0 = relu(c0.k.x + c0.k.y) * (c0.u.x - c0.u.y), g1 = relu(c1.k.x + c1.k.y) * (c1.u.x - c1.u.y);
         __syncthreads();
         const float4 up = tl[o0 - RS], dn = tl[o1 + RS];
-        const float *f = reinterpret_cast<const float *>(tl);
-        const int l0 = (o0 - 1) * 4 + 1, r0 = (o0 + 1) * 4, l1 = (o1 - 1) * 4 + 1, r1 = (o1 + 1) * 4;
-        const float ul0 = f[l0], kl0 = f[l0 + 2], ur0 = f[r0], kr0 = f[r0 + 2];
-        const float ul1 = f[l1], kl1 = f[l1 + 2], ur1 = f[r1], kr1 = f[r1 + 2];
+        float ul0 = from_left<TZL>(c0.u.y), kl0 = from_left<TZL>(c0.k.y), ur0 = from_right<TZL>(c0.u.x), kr0 = from_right<TZL>(c0.k.x);
+        float ul1 = from_left<TZL>(c1.u.y), kl1 = from_left<TZL>(c1.k.y), ur1 = from_right<TZL>(c1.u.x), kr1 = from_right<TZL>(c1.k.x);
+        if (threadIdx.x == 0) { const float4 e0 = tl[o0 - 1], e1 = tl[o1 - 1]; ul0 = e0.y; kl0 = e0.w; ul1 = e1.y; kl1 = e1.w; }
+        if (threadIdx.x == TZL - 1) { const float4 e0 = tl[o0 + 1], e1 = tl[o1 + 1]; ur0 = e0.x; kr0 = e0.z; ur1 = e1.x; kr1 = e1.z; }
         float2 sp0 = mul2(cy2, sub2(mul2(relu2(add2(make_float2(up.z, up.w), c0.k)), sub2(make_float2(up.x, up.y), c0.u)), f_mid));
         float2 sp1 = mul2(cy2, sub2(f_mid, mul2(relu2(add2(c1.k, make_float2(dn.z, dn.w))), sub2(c1.u, make_float2(dn.x, dn.y)))));
         const float fl0 = relu(kl0 + c0.k.x) * (ul0 - c0.u.x), fr0 = relu(c0.k.y + kr0) * (c0.u.y - ur0);
@@ -540,10 +553,10 @@ __global__ void __launch_bounds__(TZL *TYT, MINB) fk2c_step_v6(const StepArgs<fl
         const float gp = relu(c.k.x + c.k.y) * (c.p.x - c.p.y), gs = relu(c.b.x + c.b.y) * (c.s.x - c.s.y);
         __syncthreads();
         const float4 pu = t0[o - RS], pd = t0[o + RS], su = t1[o - RS], sd = t1[o + RS];
-        const float *f0 = reinterpret_cast<const float *>(t0), *f1 = reinterpret_cast<const float *>(t1);
-        const int l = (o - 1) * 4 + 1, r = (o + 1) * 4;
-        const float pl = f0[l], kl = f0[l + 2], pr = f0[r], kr = f0[r + 2];
-        const float sl = f1[l], bl = f1[l + 2], sr = f1[r], br = f1[r + 2];
+        float pl = from_left<TZL>(c.p.y), kl = from_left<TZL>(c.k.y), sl = from_left<TZL>(c.s.y), bl = from_left<TZL>(c.b.y);
+        float pr = from_right<TZL>(c.p.x), kr = from_right<TZL>(c.k.x), sr = from_right<TZL>(c.s.x), br = from_right<TZL>(c.b.x);
+        if (threadIdx.x == 0) { const float4 e0 = t0[o - 1], e1 = t1[o - 1]; pl = e0.y; kl = e0.w; sl = e1.y; bl = e1.w; }
+        if (threadIdx.x == TZL - 1) { const float4 e0 = t0[o + 1], e1 = t1[o + 1]; pr = e0.x; kr = e0.z; sr = e1.x; br = e1.z; }
         float2 sp = mul2(cy2, sub2(mul2(relu2(add2(make_float2(pu.z, pu.w), c.k)), sub2(make_float2(pu.x, pu.y), c.p)),
                                    mul2(relu2(add2(c.k, make_float2(pd.z, pd.w))), sub2(c.p, make_float2(pd.x, pd.y)))));
         float2 ss = mul2(ey2, sub2(mul2(relu2(add2(make_float2(su.z, su.w), c.b)), sub2(make_float2(su.x, su.y), c.s)),
@@ -623,9 +636,9 @@ __global__ void __launch_bounds__(TZL *TYT, MINB) fk_step_v6(const StepArgs<floa
         const float g0 = relu(c.k.x + c.k.y) * (c.u.x - c.u.y);
         __syncthreads();
         const float4 up = tl[o - RS], dn = tl[o + RS];
-        const float *f = reinterpret_cast<const float *>(tl);
-        const int l = (o - 1) * 4 + 1, r = (o + 1) * 4;
-        const float ul = f[l], kl = f[l + 2], ur = f[r], kr = f[r + 2];
+        float ul = from_left<TZL>(c.u.y), kl = from_left<TZL>(c.k.y), ur = from_right<TZL>(c.u.x), kr = from_right<TZL>(c.k.x);
+        if (threadIdx.x == 0) { const float4 e = tl[o - 1]; ul = e.y; kl = e.w; }
+        if (threadIdx.x == TZL - 1) { const float4 e = tl[o + 1]; ur = e.x; kr = e.z; }
         float2 sp = mul2(cy2, sub2(mul2(relu2(add2(make_float2(up.z, up.w), c.k)), sub2(make_float2(up.x, up.y), c.u)),
                                    mul2(relu2(add2(c.k, make_float2(dn.z, dn.w))), sub2(c.u, make_float2(dn.x, dn.y)))));
         const float fl = relu(kl + c.k.x) * (ul - c.u.x), fr = relu(c.k.y + kr) * (c.u.y - ur);
