@@ -391,7 +391,15 @@ static bool tma_ok(const tgtk_sim *s)
 static int effective_variant(const tgtk_sim *s)
 {
     if (s->slab_on) return 4;              // the in-kernel halo push lives in the two-voxel kernels
-    if (s->variant == 0) return (has_v5(s) && s->p.model == TGTK_MODEL_DTI) ? 6 : 4;
+    if (s->variant == 0) {
+        if (!has_v5(s)) return 4;
+        if (s->p.model == TGTK_MODEL_DTI) return 6;
+        // FK fp32 (round 2: left / right neighbours by warp shuffle instead of conflicting scalar shared-memory reads):
+        // four voxels per thread win while the arrays sit in L2 (13.5 vs 15.3 us on the atlas box), one z pair per
+        // thread beyond it (83.9 vs 85.6 us at 28 M voxels); FK_2c stays with the two-voxel kernel (level or behind)
+        if (s->p.model == TGTK_MODEL_FK) return exceeds_l2(s) ? 6 : 5;
+        return 4;
+    }
     if (s->variant == 7) return tma_ok(s) ? 7 : 4;
     if (s->variant >= 5) return has_v5(s) ? s->variant : 4;
     return s->variant;
