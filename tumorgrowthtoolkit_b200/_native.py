@@ -60,6 +60,20 @@ def lib():
             "(run __graft_entry__.build() or `make -C tumorgrowthtoolkit_b200/csrc`). "
             "There is no CPU fallback.")
     L = ctypes.CDLL(LIB_PATH)
+    if os.environ.get("TGTK_LIB_PATH"):
+        # A/B runs against an older build of the library (tools/sweep_env.py): entry points it lacks are never called there
+        class _Tolerant:
+            def __init__(self, lib):
+                object.__setattr__(self, "_lib", lib)
+
+            def __getattr__(self, name):
+                try:
+                    return getattr(self._lib, name)
+                except AttributeError:
+                    class _Missing:
+                        argtypes = restype = None
+                    return _Missing()
+        L = _Tolerant(L)
     L.tgtk_last_error.restype = ctypes.c_char_p
     L.tgtk_abi_version.restype = ctypes.c_int
     vp, dp, ip = ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)

@@ -377,6 +377,8 @@ static bool has_v5(const tgtk_sim *s)
     return s->p.dtype == TGTK_F32 && (m == TGTK_MODEL_FK || m == TGTK_MODEL_FK_2C || m == TGTK_MODEL_DTI);
 }
 
+static bool slab_kernels(const tgtk_sim *s);
+
 // 7 = FK_2c with TMA tile staging and a producer warp (tgtk_kernels_tma.cuh); needs 16-byte global strides
 static bool tma_ok(const tgtk_sim *s)
 {
@@ -563,6 +565,17 @@ template <typename T> static cudaError_t launch_step(tgtk_sim *s)
         }
     }
     if (s->sy != s->p.Z) s->pads_dirty = true;   // no other kernel maintains the z = 0 mirror
+    // the fused slab driver (and the serpentine sweep) run dedicated instantiations of the two-voxel kernels, 32 x 4 threads
+    if (s->lx > 0 && effective_variant(s) == 4 && slab_kernels(s)) {
+        switch (s->p.model) {
+        case TGTK_MODEL_FK: return launch_v4(s, fk_step_v4<T, 32, 4, 8, 1>, a, s->lx);
+        case TGTK_MODEL_DTI: return launch_v4(s, dti_step_v4<T, 32, 4, 8, 1>, a, s->lx);
+        case TGTK_MODEL_FK_2C:
+            if (sizeof(T) == 8) return launch_v4(s, fk2c_step_v4<T, 32, 4, 4, 0, 1>, a, s->lx);
+            return launch_v4(s, fk2c_step_v4<T, 32, 4, 6, 0, 1>, a, s->lx);
+        default: break;
+        }
+    }
     if (s->lx > 0 && effective_variant(s) == 4 && s->p.model == TGTK_MODEL_FK) {
         if (s->block.x == 16) return launch_v4(s, fk_step_v4<T, 16, 8, 8>, a, s->lx);
         else if (s->block.y == 4) return launch_v4(s, fk_step_v4<T, 32, 4, 8>, a, s->lx);
@@ -691,6 +704,20 @@ static const void *v6_kernel(int model, int minb)
     return (minb == 0 || minb >= 6) ? (const void *)fk2c_step_v6<16, 8, 6> : (const void *)fk2c_step_v6<16, 8, 4>;
 }
 
+static bool slab_kernels(const tgtk_sim *s)
+{
+    const int m = s->p.model;
+    return (s->slab_on || s->zigzag) && (m == TGTK_MODEL_FK || m == TGTK_MODEL_FK_2C || m == TGTK_MODEL_DTI);
+}
+
+static const void *v4_slab_kernel(int model, int dtype)
+{
+    const bool d = (dtype == TGTK_F64);
+    if (model == TGTK_MODEL_FK) return d ? (const void *)fk_step_v4<double, 32, 4, 8, 1> : (const void *)fk_step_v4<float, 32, 4, 8, 1>;
+    if (model == TGTK_MODEL_DTI) return d ? (const void *)dti_step_v4<double, 32, 4, 8, 1> : (const void *)dti_step_v4<float, 32, 4, 8, 1>;
+    return d ? (const void *)fk2c_step_v4<double, 32, 4, 4, 0, 1> : (const void *)fk2c_step_v4<float, 32, 4, 6, 0, 1>;
+}
+
 static const void *v4_kernel(int model, int dtype, int rows, int minb)
 {
     if (rows == 16) {   // 16-wide tiles
@@ -776,7 +803,9 @@ static int configure_launch(tgtk_sim *s)
             narrow = s->force_tz ? (s->force_tz == 16) : (w16 * (1.0 + s->narrow_penalty) < w32);
         }
         if (four || zp1) narrow = false;
-        const int v4rows = (narrow || four || zp1) ? 8 : ((s->v4_threads == 128) ? 4 : 8);          // thread rows; voxel rows = 2x
+        const bool slabk = (variant == 4) && slab_kernels(s);
+        if (slabk) narrow = false;
+        const int v4rows = slabk ? 4 : (narrow || four || zp1) ? 8 : ((s->v4_threads == 128) ? 4 : 8);   // thread rows; voxel rows = 2x
         const int tz = two_rows ? (narrow ? 16 : 32) : best_tz, ty = zp1 ? 8 : two_rows ? 2 * v4rows : 256 / tz;   // voxels per tile
         const int tiles = ((p.Z + tz - 1) / tz) * ((p.Y + ty - 1) / ty);
         // Segment length: trade the tail of the last wave (blocks / resident slots not an
@@ -784,6 +813,7 @@ static int configure_launch(tgtk_sim *s)
         int per_sm = 2, sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
         const void *fn = four ? v5_kernel(p.model, s->minb) : zp1 ? v6_kernel(p.model, s->minb)
+                         : slabk ? v4_slab_kernel(p.model, p.dtype)
                          : two_rows ? v4_kernel(p.model, p.dtype, narrow ? 16 : v4rows, s->minb)
                          : (variant >= 3)
                              ? ((p.dtype == TGTK_F64) ? v3_kernel<double>(p.model, tz == 32, s->pf == 1 ? 14 : s->minb) : v3_kernel<float>(p.model, tz == 32, s->pf == 1 ? 14 : s->minb))
@@ -1215,9 +1245,14 @@ int tgtk_sim_create_ex(tgtk_sim **out, const tgtk_params *params, int device, vo
     }
     s->n = (size_t)p.X * p.Y * p.Z;
     s->elem = (p.dtype == TGTK_F64) ? 8 : 4;
-    // rows have an even pitch: every (row, even z) pair of fp32 is 8-byte aligned for the z-pair kernels, and every
-    // row of either type starts on a 16-byte boundary, which TMA tensor maps require of the global strides
-    s->sy = p.Z + (p.Z & 1);
+    // fp32 rows have an even pitch: every (row, even z) pair is 8-byte aligned for the z-pair kernels.  fp64 rows are
+    // dense -- except when the TMA-staged kernel is asked for at creation (TGTK_VARIANT=7), whose tensor maps need
+    // 16-byte global strides; the padded fp64 pitch costs the default kernels 1-2 % (profiles/r2_sweep_misc.txt)
+    {
+        const char *v = getenv("TGTK_VARIANT"), *e = getenv("TGTK_EVEN_PITCH64");
+        const bool even64 = e ? atoi(e) != 0 : (v && atoi(v) == 7);
+        s->sy = p.Z + ((p.dtype == TGTK_F32 || even64) ? (p.Z & 1) : 0);
+    }
     s->sx = (int64_t)p.Y * s->sy;
     s->nfields = (p.model == TGTK_MODEL_FK_2C || p.model == TGTK_MODEL_FK2C_COEF12) ? 3 : 1;
     switch (p.model) {

@@ -31,9 +31,8 @@ template <typename T> struct StepArgs {
     const T *coef[12];     // model dependent, see tgtk_api.cu
     T cx, cy, cz;          // FK/FK_2c: Dw/h^2 ; DTI/COEF6/FACES: 1/h^2
     T ex, ey, ez;          // FK_2c: Ds/h^2
-    T hx, hy, hz, gx, gy, gz;   // the same six constants for the two-voxel kernels, which take max(x, 0) as relu2(x) = x + |x| = 2 max(x, 0)
-                                // in fp64 (ONE fp64-pipe instruction, |x| is an operand modifier, instead of a compare and two selects): the
-                                // constants carry the factor 1/2 -- exact, a power of two -- so every product is bit for bit the same
+    T hx, hy, hz, gx, gy, gz;   // the same six constants for the two-voxel kernels; with -DTGTK_RELU2 (experiment, off) they carry a
+                                // factor 1/2 and max(x, 0) is taken as x + |x| = 2 max(x, 0): exact, every product bit for bit the same
     T dt, rho;
     T th_necro, lambda_np, sigma_np, lambda_s;
     double vol_scale_p;    // dx*dy*dz
@@ -247,8 +246,10 @@ __device__ __forceinline__ double relu(double x)
 }
 __device__ __forceinline__ float relu(float x) { return fmaxf(x, 0.0f); }
 
-// 2 max(x, 0) for the two-voxel kernels (see StepArgs::hx): fp64 x + |x|, fp32 2 fmaxf (one FMNMX + the factor in the constant)
-#ifndef TGTK_NO_RELU2
+// 2 max(x, 0) for the two-voxel kernels (see StepArgs::hx): x + |x|.  Compile-time experiment (-DTGTK_RELU2), OFF by
+// default: it removes 18 ALU instructions per FK_2c voxel but adds 9 to the fp64 pipe, and measured 2.4 % SLOWER on the
+// B200 (profiles/r2_sweep_misc.txt) -- the kernel is not short of issue slots, it is short of fp64-pipe latency cover.
+#ifdef TGTK_RELU2
 template <typename T> struct Relu2 { static constexpr double scale = 0.5; };
 __device__ __forceinline__ double relu2(double x) { return x + fabs(x); }
 __device__ __forceinline__ float relu2(float x) { return x + fabsf(x); }

@@ -285,7 +285,10 @@ struct Stage2 {
     int so, hs;          // shared-memory slot of the upper-row voxel (the lower one is so + RS) / ring slot
 };
 
-template <typename T, int TZ, int TYT, int RS>
+// SLAB = 1: the instantiation the fused slab driver launches (restricted plane range, boundary segments last, halo push,
+// optional serpentine sweep).  The ordinary instantiation carries none of it: its mere presence in the plane loop cost
+// 5-6 % on FK / FK_2c (round-2 bisect, profiles/r2_sweep_misc.txt).
+template <typename T, int TZ, int TYT, int RS, int SLAB = 0>
 __device__ __forceinline__ Stage2 stage2_setup(const StepArgs<T> &a, int lx)
 {
     constexpr int TYV = 2 * TYT;          // voxel rows per tile
@@ -298,9 +301,14 @@ __device__ __forceinline__ Stage2 stage2_setup(const StepArgs<T> &a, int lx)
     // fused slab mode: the two segments that read a ghost plane get the highest block indices -- they are scheduled
     // last, when the neighbours' words have long arrived
     int seg = blockIdx.z;
-    if (a.slab && gridDim.z > 2) seg = (seg + 2 < (int)gridDim.z) ? seg + 1 : (seg + 2 == (int)gridDim.z ? 0 : seg);
-    g.x0 = a.x_lo + seg * lx;
-    g.x1 = min(g.x0 + lx, a.x_hi);
+    if (SLAB) {
+        if (a.slab && gridDim.z > 2) seg = (seg + 2 < (int)gridDim.z) ? seg + 1 : (seg + 2 == (int)gridDim.z ? 0 : seg);
+        g.x0 = a.x_lo + seg * lx;
+        g.x1 = min(g.x0 + lx, a.x_hi);
+    } else {
+        g.x0 = seg * lx;
+        g.x1 = min(g.x0 + lx, a.X);
+    }
     g.sx = (uint32_t)a.sx;
     g.wrap_back = (uint32_t)(a.X - 1) * g.sx;
     const uint32_t sy = (uint32_t)a.sy, base = (uint32_t)g.x0 * g.sx;
@@ -331,12 +339,12 @@ struct March2 {
     uint32_t wrapd;
 };
 
-template <typename T> __device__ __forceinline__ March2 march2_setup(const StepArgs<T> &a, Stage2 &g, int par)
+template <typename T, int SLAB> __device__ __forceinline__ March2 march2_setup(const StepArgs<T> &a, Stage2 &g, int par)
 {
     March2 m;
-    // serpentine sweep: odd steps march downwards, so a step starts on the planes the previous step wrote last --
-    // the part of the state that is still in L2 (the ping-pong parity is the step's parity)
-    m.down = a.zigzag && (par & 1);
+    // serpentine sweep (TGTK_ZIGZAG=1, measured +-1 %): odd steps march downwards, so a step starts on the planes the
+    // previous step wrote last -- the part of the state that is still in L2 (the ping-pong parity is the step's parity)
+    m.down = SLAB && a.zigzag && (par & 1);
     m.n = g.x1 - g.x0;
     m.xs = g.x0;
     m.dx = 1;
@@ -362,7 +370,7 @@ template <typename T> struct Vox2c { T p, n, s, b, k; };
 // LL = 1 ("late loads"): the own-column values of the next plane are requested AFTER the barrier instead of at the top
 // of the step -- their registers are then not live across the in-plane section, which is what lets the kernel fit
 // 5 blocks per SM (96 registers) without spilling; the bulk L2 prefetch keeps the shortened distance cheap.
-template <typename T, int TZ, int TYT, int MINB = 2, int LL = 0>
+template <typename T, int TZ, int TYT, int MINB = 2, int LL = 0, int SLAB = 0>
 __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> a, const int lx)
 {
     constexpr int TYV = 2 * TYT, RS = TZ + 2, PL = (TYV + 2) * RS;
@@ -377,15 +385,15 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> 
     T *__restrict__ So = a.buf[sc.par ^ 1][2];
     const T *__restrict__ kc = a.coef[0];
     const T *__restrict__ bc = a.coef[1];
-    Stage2 g = stage2_setup<T, TZ, TYT, RS>(a, lx);
-    const March2 mm = march2_setup(a, g, sc.par);
+    Stage2 g = stage2_setup<T, TZ, TYT, RS, SLAB>(a, lx);
+    const March2 mm = march2_setup<T, SLAB>(a, g, sc.par);
     const T closed = -Big<T>::v;
     auto keff = [&](T pq, T nq, T kq) { return (pq + nq <= a.th_necro) ? kq : closed; };
     auto load = [&](Vox2c<T> &v, uint32_t off) { v.p = P[off]; v.n = N[off]; v.s = S[off]; v.b = bc[off]; v.k = kc[off]; };
     double sP = 0.0, sN = 0.0;
     griddep_launch();
     griddep_wait();
-    const SlabCtl sl = slab_begin(a, g.x0, g.x1);
+    const SlabCtl sl = SLAB ? slab_begin(a, g.x0, g.x1) : SlabCtl{false, false, 0};
     auto push = [&](T *const *peer, uint32_t off, T pn0, T nn0, T sn0, T pn1, T nn1, T sn1) {
         if (g.valid0) { peer[0][g.c0 + off] = pn0; peer[1][g.c0 + off] = nn0; peer[2][g.c0 + off] = sn0; }
         if (g.valid1) { peer[0][g.c1 + off] = pn1; peer[1][g.c1 + off] = nn1; peer[2][g.c1 + off] = sn1; }
@@ -478,8 +486,8 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> 
             Po[g.c1] = pn1; No[g.c1] = nn1; So[g.c1] = sn1;
             if (cnt) { sP += (double)pn1; sN += (double)nn1; }
         }
-        if (sl.lo && x == a.x_lo) { push(a.peer_lo[sc.par ^ 1], a.off_lo, pn0, nn0, sn0, pn1, nn1, sn1); }
-        if (sl.hi && x == a.x_hi - 1) { push(a.peer_hi[sc.par ^ 1], a.off_hi, pn0, nn0, sn0, pn1, nn1, sn1); }
+        if (SLAB && sl.lo && x == a.x_lo) { push(a.peer_lo[sc.par ^ 1], a.off_lo, pn0, nn0, sn0, pn1, nn1, sn1); }
+        if (SLAB && sl.hi && x == a.x_hi - 1) { push(a.peer_hi[sc.par ^ 1], a.off_hi, pn0, nn0, sn0, pn1, nn1, sn1); }
         fp_lo0 = fp_hi0; fs_lo0 = fs_hi0; fp_lo1 = fp_hi1; fs_lo1 = fs_hi1;
         g.c0 = n0; g.c1 = n1;
         buf ^= 1;
@@ -495,7 +503,7 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> 
 // ---- FK, two voxels per thread (see fk2c_step_v4) -------------------------------------------------
 template <typename T> struct VoxFk { T u, k; };
 
-template <typename T, int TZ, int TYT, int MINB = 4>
+template <typename T, int TZ, int TYT, int MINB = 4, int SLAB = 0>
 __global__ void __launch_bounds__(TZ *TYT, MINB) fk_step_v4(const StepArgs<T> a, const int lx)
 {
     constexpr int TYV = 2 * TYT, RS = TZ + 2, PL = (TYV + 2) * RS;
@@ -505,12 +513,12 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk_step_v4(const StepArgs<T> a,
     const T *__restrict__ u = a.buf[sc.par][0];
     T *__restrict__ out = a.buf[sc.par ^ 1][0];
     const T *__restrict__ kc = a.coef[0];
-    Stage2 g = stage2_setup<T, TZ, TYT, RS>(a, lx);
-    const March2 mm = march2_setup(a, g, sc.par);
+    Stage2 g = stage2_setup<T, TZ, TYT, RS, SLAB>(a, lx);
+    const March2 mm = march2_setup<T, SLAB>(a, g, sc.par);
     double s = 0.0;
     griddep_launch();
     griddep_wait();
-    const SlabCtl sl = slab_begin(a, g.x0, g.x1);
+    const SlabCtl sl = SLAB ? slab_begin(a, g.x0, g.x1) : SlabCtl{false, false, 0};
     auto push = [&](T *const *peer, uint32_t off, T v0, T v1) {
         if (g.valid0) peer[0][g.c0 + off] = v0;
         if (g.valid1) peer[0][g.c1 + off] = v1;
@@ -558,8 +566,8 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk_step_v4(const StepArgs<T> a,
         const bool cnt = counts(a, x);
         if (g.valid0) { out[g.c0] = un0; if (cnt) s += (double)un0; }
         if (g.valid1) { out[g.c1] = un1; if (cnt) s += (double)un1; }
-        if (sl.lo && x == a.x_lo) { push(a.peer_lo[sc.par ^ 1], a.off_lo, un0, un1); }
-        if (sl.hi && x == a.x_hi - 1) { push(a.peer_hi[sc.par ^ 1], a.off_hi, un0, un1); }
+        if (SLAB && sl.lo && x == a.x_lo) { push(a.peer_lo[sc.par ^ 1], a.off_lo, un0, un1); }
+        if (SLAB && sl.hi && x == a.x_hi - 1) { push(a.peer_hi[sc.par ^ 1], a.off_hi, un0, un1); }
         f_lo0 = f_hi0; f_lo1 = f_hi1;
         g.c0 = n0; g.c1 = n1;
         buf ^= 1;
@@ -575,7 +583,7 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk_step_v4(const StepArgs<T> a,
 // ---- FK_DTI, two voxels per thread (reference rounding order, bitwise equal to dti_step_v3) ----------
 template <typename T> struct VoxDti { T u, d0, d1, d2; };
 
-template <typename T, int TZ, int TYT, int MINB = 4>
+template <typename T, int TZ, int TYT, int MINB = 4, int SLAB = 0>
 __global__ void __launch_bounds__(TZ *TYT, MINB) dti_step_v4(const StepArgs<T> a, const int lx)
 {
     using R = Rn<T>;
@@ -588,15 +596,15 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) dti_step_v4(const StepArgs<T> a
     const T *__restrict__ dxa = a.coef[0];
     const T *__restrict__ dya = a.coef[1];
     const T *__restrict__ dza = a.coef[2];
-    Stage2 g = stage2_setup<T, TZ, TYT, RS>(a, lx);
-    const March2 mm = march2_setup(a, g, sc.par);
+    Stage2 g = stage2_setup<T, TZ, TYT, RS, SLAB>(a, lx);
+    const March2 mm = march2_setup<T, SLAB>(a, g, sc.par);
     double s = 0.0;
     auto load = [&](VoxDti<T> &v, uint32_t off) { v.u = u[off]; v.d0 = dxa[off]; v.d1 = dya[off]; v.d2 = dza[off]; };
 
     VoxDti<T> A0, A1, B0, B1;
     griddep_launch();
     griddep_wait();
-    const SlabCtl sl = slab_begin(a, g.x0, g.x1);
+    const SlabCtl sl = SLAB ? slab_begin(a, g.x0, g.x1) : SlabCtl{false, false, 0};
     auto push = [&](T *const *peer, uint32_t off, T v0, T v1) {
         if (g.valid0) peer[0][g.c0 + off] = v0;
         if (g.valid1) peer[0][g.c1 + off] = v1;
@@ -641,8 +649,8 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) dti_step_v4(const StepArgs<T> a
         const bool cnt = counts(a, x);
         if (g.valid0) { out[g.c0] = un0; if (cnt) s += (double)un0; }
         if (g.valid1) { out[g.c1] = un1; if (cnt) s += (double)un1; }
-        if (sl.lo && x == a.x_lo) { push(a.peer_lo[sc.par ^ 1], a.off_lo, un0, un1); }
-        if (sl.hi && x == a.x_hi - 1) { push(a.peer_hi[sc.par ^ 1], a.off_hi, un0, un1); }
+        if (SLAB && sl.lo && x == a.x_lo) { push(a.peer_lo[sc.par ^ 1], a.off_lo, un0, un1); }
+        if (SLAB && sl.hi && x == a.x_hi - 1) { push(a.peer_hi[sc.par ^ 1], a.off_hi, un0, un1); }
         um0 = c0.u; um1 = c1.u;
         g.c0 = n0; g.c1 = n1;
         buf ^= 1;
