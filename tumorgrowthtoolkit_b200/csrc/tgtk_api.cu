@@ -1252,6 +1252,7 @@ int tgtk_sim_create_ex(tgtk_sim **out, const tgtk_params *params, int device, vo
         const char *v = getenv("TGTK_VARIANT"), *e = getenv("TGTK_EVEN_PITCH64");
         const bool even64 = e ? atoi(e) != 0 : (v && atoi(v) == 7);
         s->sy = p.Z + ((p.dtype == TGTK_F32 || even64) ? (p.Z & 1) : 0);
+        if (even64 && p.dtype == TGTK_F32) s->sy = (p.Z + 3) / 4 * 4;      // 16-byte rows in fp32 too
     }
     s->sx = (int64_t)p.Y * s->sy;
     s->nfields = (p.model == TGTK_MODEL_FK_2C || p.model == TGTK_MODEL_FK2C_COEF12) ? 3 : 1;
