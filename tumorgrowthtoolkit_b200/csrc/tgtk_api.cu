@@ -118,6 +118,7 @@ struct tgtk_sim {
     unsigned partials_cap = 0;
     // temporal blocking (tgtk_kernels_tb.cuh): two steps per launch where a kernel exists (FK, FK_DTI) and the
     // run is host-scheduled or speculative.  TGTK_TB: 1 on, 0 off, -1 auto (fp64 boxes of more than twice the L2)
+    int closed_skip = 1;   // exact per-warp shortcuts of the two-voxel FK / FK_2c kernels (TGTK_CLOSED_SKIP=0: off)
     int zigzag = 0;        // serpentine sweep of the two-voxel kernels (TGTK_ZIGZAG=1): measured +-1 %, off by default
     int tb = -1;
     int tb_rows = 18;      // thread rows of the two-step kernel's block: 18 (16 output rows, 576 threads) or 10 (8, 320)
@@ -350,6 +351,7 @@ template <typename T> static void fill_args(const tgtk_sim *s, StepArgs<T> &a)
     a.x_lo = 0;
     a.x_hi = p.X;
     a.zigzag = s->zigzag;
+    a.skip = s->closed_skip;
     a.slab = 0;
     if (s->slab_on) {
         a.slab = 1;
@@ -396,10 +398,9 @@ static int effective_variant(const tgtk_sim *s)
     if (s->variant == 0) {
         if (!has_v5(s)) return 4;
         if (s->p.model == TGTK_MODEL_DTI) return 6;
-        // FK fp32 (round 2: left / right neighbours by warp shuffle instead of conflicting scalar shared-memory reads):
-        // four voxels per thread win while the arrays sit in L2 (13.5 vs 15.3 us on the atlas box), one z pair per
-        // thread beyond it (83.9 vs 85.6 us at 28 M voxels); FK_2c stays with the two-voxel kernel (level or behind)
-        if (s->p.model == TGTK_MODEL_FK) return exceeds_l2(s) ? 6 : 5;
+        // FK / FK_2c fp32: the two-voxel kernels.  Round 2 moved the z-pair kernels' left / right neighbours to warp shuffles,
+        // which makes them 13 % faster than the two-voxel FK kernel on all-tissue random boxes -- but on the atlas, where 60 %
+        // of the box is background, the two-voxel kernel's closed-warp shortcut wins (281 vs 267 GLUPS): they stay opt-in
         return 4;
     }
     if (s->variant == 7) return tma_ok(s) ? 7 : 4;
@@ -1277,6 +1278,7 @@ int tgtk_sim_create_ex(tgtk_sim **out, const tgtk_params *params, int device, vo
     if (const char *v = getenv("TGTK_PDL")) s->pdl = atoi(v);
     if (const char *v = getenv("TGTK_TB")) s->tb = atoi(v);
     if (const char *v = getenv("TGTK_ZIGZAG")) s->zigzag = atoi(v) != 0;
+    if (const char *v = getenv("TGTK_CLOSED_SKIP")) s->closed_skip = atoi(v) != 0;
     if (const char *v = getenv("TGTK_TB_ROWS")) s->tb_rows = atoi(v);
     if (const char *v = getenv("TGTK_TMA_ROWS")) s->tma_rows = (atoi(v) == 8) ? 8 : 4;
     if (const char *v = getenv("TGTK_TMA_STAGES")) s->tma_stages = (atoi(v) == 2) ? 2 : (atoi(v) == 4) ? 4 : 3;

@@ -62,6 +62,8 @@ template <typename T> struct StepArgs {
     // planes [x_lo, x_hi) of axis 0 are computed by this launch (two-voxel kernels; default: the whole box)
     int x_lo, x_hi;
     int zigzag;               // two-voxel kernels: odd steps march axis 0 downwards (L2 reuse of what the previous step wrote last)
+    int skip;                 // two-voxel FK / FK_2c kernels: exact per-warp shortcuts for warps that hold no tumour / lie outside
+                              // the tissue (TGTK_CLOSED_SKIP=0 switches them off, e.g. to measure the dense path)
     // Fused slab mode (tgtk_nccl.inc, one rank per GPU, axis 0 decomposed, one ghost plane per side): the blocks
     // that compute the rank's lowest / highest owned plane ALSO store it into the neighbouring rank's ghost plane
     // (peer-mapped memory, NVLink).  A launch's stores are visible system-wide when the launch has completed, so

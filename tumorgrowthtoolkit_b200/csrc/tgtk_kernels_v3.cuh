@@ -441,8 +441,31 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> 
             l2_prefetch_strip(S, q, pf.count, pf.total); l2_prefetch_strip(kc, q, pf.count, pf.total);
             l2_prefetch_strip(bc, q, pf.count, pf.total);
         }
-        // work that needs neither neighbours nor plane x+1
-        const T H0 = heaviside50_fast(c0.s, a.sigma_np), H1 = heaviside50_fast(c1.s, a.sigma_np);
+        // Two exact per-warp shortcuts (decided by warp votes, so nothing diverges; TGTK_CLOSED_SKIP=0 switches them off
+        // at run time for A/B runs).  (1) The smooth Heaviside (28 fp64-pipe instructions per voxel: exp, reciprocal)
+        // only ever multiplies P and the new P: a warp whose 64 voxels all hold P == 0 skips it -- 0 * H = 0 for the
+        // finite H of a finite S.  (2) A voxel outside the tissue has b = k = "closed", so every one of its faces
+        // carries the coefficient max(closed + k', 0) = 0 whatever the neighbour holds; with P == 0 on top, the
+        // reference's update returns P' = 0, N' = N, S' = S bit for bit (0 * finite = +-0; x + +-0 = x).  A warp whose
+        // 64 voxels are all of that kind -- 60 % of the cropped atlas box is background -- still loads, publishes its
+        // tile rows for the neighbouring warps, takes the barrier and STORES its voxels (the HBM traffic is unchanged),
+        // but skips the shared-memory reads and the arithmetic.
+        const bool warp_has_p = !a.skip || __any_sync(0xffffffffu, (c0.p != T(0)) || (c1.p != T(0)));
+        const bool warp_closed = !warp_has_p && __all_sync(0xffffffffu, (c0.b == closed) && (c1.b == closed));
+        T pn0, pn1, nn0, nn1, sn0, sn1;
+        if (warp_closed) {
+            __syncthreads();
+            if (LL) {
+                load(p0, n0);
+                load(p1, n1);
+            }
+            p0.k = keff(p0.p, p0.n, p0.k);
+            p1.k = keff(p1.p, p1.n, p1.k);
+            pn0 = c0.p; pn1 = c1.p; nn0 = c0.n; nn1 = c1.n; sn0 = c0.s; sn1 = c1.s;
+            fp_lo0 = fs_lo0 = fp_lo1 = fs_lo1 = T(0);      // the faces towards the next plane are closed from this side
+        } else {
+        T H0 = T(0), H1 = T(0);
+        if (warp_has_p) { H0 = heaviside50_fast(c0.s, a.sigma_np); H1 = heaviside50_fast(c1.s, a.sigma_np); }
         const T react0 = a.rho * (c0.s * c0.p) * ((T(1) - c0.p) - c0.n) - (a.lambda_np * c0.p) * H0;
         const T react1 = a.rho * (c1.s * c1.p) * ((T(1) - c1.p) - c1.n) - (a.lambda_np * c1.p) * H1;
         // the face between the two own rows: no shared memory involved
@@ -474,9 +497,15 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> 
         sp1 += a.hx * (fp_lo1 - fp_hi1);
         ss0 += a.gx * (fs_lo0 - fs_hi0);
         ss1 += a.gx * (fs_lo1 - fs_hi1);
-        const T pn0 = c0.p + a.dt * (sp0 + react0), pn1 = c1.p + a.dt * (sp1 + react1);
-        const T nn0 = c0.n + a.dt * ((a.lambda_np * pn0) * H0), nn1 = c1.n + a.dt * ((a.lambda_np * pn1) * H1);
-        const T sn0 = c0.s + a.dt * (ss0 - (a.lambda_s * c0.s) * pn0), sn1 = c1.s + a.dt * (ss1 - (a.lambda_s * c1.s) * pn1);
+        pn0 = c0.p + a.dt * (sp0 + react0); pn1 = c1.p + a.dt * (sp1 + react1);
+        // P has just entered a warp that held none (the front moves one voxel per step): now the Heaviside is needed
+        if (!warp_has_p && __any_sync(0xffffffffu, (pn0 != T(0)) || (pn1 != T(0)))) {
+            H0 = heaviside50_fast(c0.s, a.sigma_np); H1 = heaviside50_fast(c1.s, a.sigma_np);
+        }
+        nn0 = c0.n + a.dt * ((a.lambda_np * pn0) * H0); nn1 = c1.n + a.dt * ((a.lambda_np * pn1) * H1);
+        sn0 = c0.s + a.dt * (ss0 - (a.lambda_s * c0.s) * pn0); sn1 = c1.s + a.dt * (ss1 - (a.lambda_s * c1.s) * pn1);
+        fp_lo0 = fp_hi0; fs_lo0 = fs_hi0; fp_lo1 = fp_hi1; fs_lo1 = fs_hi1;
+        }
         const bool cnt = counts(a, x);
         if (g.valid0) {
             Po[g.c0] = pn0; No[g.c0] = nn0; So[g.c0] = sn0;
@@ -488,7 +517,6 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk2c_step_v4(const StepArgs<T> 
         }
         if (SLAB && sl.lo && x == a.x_lo) { push(a.peer_lo[sc.par ^ 1], a.off_lo, pn0, nn0, sn0, pn1, nn1, sn1); }
         if (SLAB && sl.hi && x == a.x_hi - 1) { push(a.peer_hi[sc.par ^ 1], a.off_hi, pn0, nn0, sn0, pn1, nn1, sn1); }
-        fp_lo0 = fp_hi0; fs_lo0 = fs_hi0; fp_lo1 = fp_hi1; fs_lo1 = fs_hi1;
         g.c0 = n0; g.c1 = n1;
         buf ^= 1;
     };
@@ -550,6 +578,17 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk_step_v4(const StepArgs<T> a,
             const uint32_t q = l2_strip_at(a, pf, x, mm.dx);
             l2_prefetch_strip(u, q, pf.count, pf.total); l2_prefetch_strip(kc, q, pf.count, pf.total);
         }
+        // a warp whose 64 voxels all lie outside the tissue (k = "closed": every face coefficient is max(closed + k', 0) = 0)
+        // and hold u == 0 returns u' = 0 in the reference's arithmetic: it loads, publishes, takes the barrier and stores,
+        // but skips the shared-memory reads and the arithmetic (see fk2c_step_v4)
+        const T closed_k = -Big<T>::v;
+        const bool warp_closed = a.skip && __all_sync(0xffffffffu, (c0.k == closed_k) && (c1.k == closed_k) && (c0.u == T(0)) && (c1.u == T(0)));
+        T un0, un1;
+        if (warp_closed) {
+            __syncthreads();
+            un0 = c0.u; un1 = c1.u;
+            f_lo0 = f_lo1 = T(0);
+        } else {
         const T react0 = a.rho * c0.u * (T(1) - c0.u), react1 = a.rho * c1.u * (T(1) - c1.u);
         const T f_mid = relu2(c0.k + c1.k) * (c0.u - c1.u);
         __syncthreads();
@@ -562,13 +601,14 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) fk_step_v4(const StepArgs<T> a,
         const T f_hi0 = relu2(c0.k + p0.k) * (c0.u - p0.u), f_hi1 = relu2(c1.k + p1.k) * (c1.u - p1.u);
         sp0 += a.hx * (f_lo0 - f_hi0);
         sp1 += a.hx * (f_lo1 - f_hi1);
-        const T un0 = c0.u + a.dt * (sp0 + react0), un1 = c1.u + a.dt * (sp1 + react1);
+        un0 = c0.u + a.dt * (sp0 + react0); un1 = c1.u + a.dt * (sp1 + react1);
+        f_lo0 = f_hi0; f_lo1 = f_hi1;
+        }
         const bool cnt = counts(a, x);
         if (g.valid0) { out[g.c0] = un0; if (cnt) s += (double)un0; }
         if (g.valid1) { out[g.c1] = un1; if (cnt) s += (double)un1; }
         if (SLAB && sl.lo && x == a.x_lo) { push(a.peer_lo[sc.par ^ 1], a.off_lo, un0, un1); }
         if (SLAB && sl.hi && x == a.x_hi - 1) { push(a.peer_hi[sc.par ^ 1], a.off_hi, un0, un1); }
-        f_lo0 = f_hi0; f_lo1 = f_hi1;
         g.c0 = n0; g.c1 = n1;
         buf ^= 1;
     };
@@ -643,6 +683,8 @@ __global__ void __launch_bounds__(TZ *TYT, MINB) dti_step_v4(const StepArgs<T> a
             l2_prefetch_strip(dya, q, pf.count, pf.total); l2_prefetch_strip(dza, q, pf.count, pf.total);
         }
         __syncthreads();
+        // (no closed-warp shortcut here: FK_DTI streams at 0.85 of the HBM roofline, and the vote over eight compares cost
+        // 3 % on the atlas box -- profiles/r2_sweep_misc.txt)
         // um* = the plane behind the march, p*.u the plane ahead: x-1 / x+1 when marching up, swapped when marching down
         const T un0 = one(c0, mm.down ? p0.u : um0, mm.down ? um0 : p0.u, tl[o0 - RS], c1.u, tl[o0 - 1], tl[o0 + 1]);
         const T un1 = one(c1, mm.down ? p1.u : um1, mm.down ? um1 : p1.u, c0.u, tl[o1 + RS], tl[o1 - 1], tl[o1 + 1]);
