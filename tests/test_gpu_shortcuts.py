@@ -42,7 +42,7 @@ def test_fk2c_shortcuts_change_nothing(shape, precision):
     wm, gm, u0, _ = _phantom(shape, 1)
     assert (wm + gm < 0.1).mean() > 0.3 and (u0 > 0).sum() > 20        # background and a seed are both there
     S0 = np.where(wm + gm >= 0.1, 1.0, 0.0)
-    args = (u0, np.zeros_like(u0), S0, wm, gm, 0.1, 0.9, 0.9, 100.0, 1.3, 0.3, 0.35, 0.5, 0.05, 0.03, 1.0, 1.0, 1.0, 90)
+    args = (u0, np.zeros_like(u0), S0, wm, gm, 0.1, 0.9, 0.9, 100.0, 1.3, 0.5, 0.35, 0.5, 2.0, 0.03, 1.0, 1.0, 1.0, 90)
     rec = np.arange(0, 90, 11)
     a = _run(_loop.fk2c_loop, *args, skip="1", precision=precision, record_steps=rec)
     b = _run(_loop.fk2c_loop, *args, skip="0", precision=precision, record_steps=rec)
@@ -51,7 +51,7 @@ def test_fk2c_shortcuts_change_nothing(shape, precision):
         for p, q in zip(a["snapshots"][k], b["snapshots"][k]):
             assert np.array_equal(p, q)
     assert a["volume"] == b["volume"]
-    assert (a["state"]["N"] > 0).any()                                     # necrosis developed: the Heaviside mattered
+    assert a["state"]["N"].max() > 0.1                                     # necrosis developed: the Heaviside mattered
 
 
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
