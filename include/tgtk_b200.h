@@ -127,8 +127,16 @@ int tgtk_sim_set_variant(tgtk_sim *sim, int variant);
 /* What the launch heuristics chose, for logs and benchmarks: out[0] kernel family in effect, out[1] planes
  * per block segment, out[2] L2 prefetch distance in planes (0 = off), out[3] programmatic dependent launch
  * (0/1), out[4..6] grid x, y, z, out[7] threads per block, out[8] temporal blocking: time steps per
- * launch (1 or 2), out[9] reserved (0). */
+ * launch (1 or 2), out[9] work items of a sparse launch (0: dense grid; see tgtk_sim_sparse_info). */
 int tgtk_sim_get_tuning(tgtk_sim *sim, int32_t out[10]);
+/* Sparse launches (FK_2c; TGTK_SPARSE = 1 on / 0 off / unset: boxes beyond L2 with at least 10 % dead space).  The solvers
+ * run on the bounding box of the brain, most of which is background (FK_2c.py:170-185).  A voxel outside the tissue with
+ * P = N = 0 is a fixed point of the reference's update that no neighbour can disturb (all its face coefficients are 0), so
+ * the 2 x 32 voxel tiles that consist of such voxels only are neither loaded, computed nor stored, and the launch grid is a
+ * work list over the rest: same results bit for bit, proportionally less HBM traffic.  Decided from the current state the
+ * next time tgtk_sim_run is called after an upload (or by this call).  out[0] work items per launch (0: dense launches),
+ * out[1] voxels in live tiles, out[2] voxels of the box, out[3] words of the tile mask. */
+int tgtk_sim_sparse_info(tgtk_sim *sim, int64_t out[4]);
 
 /* Slab decomposition support.  set_sum_range: only planes [x0, x1) of axis 0 count towards the
  * volume (a rank's owned planes; its ghost planes are stepped but not summed).  buffer_ptr: device

@@ -40,6 +40,8 @@ def _finish(sim, nsteps, record_steps, fields, names, output=None):
                steps_run=int(st.steps_run), stop=stop,
                t_stop=(int(st.stop_step) if st.stop_reason == nat.STOP_VOLUME else None),
                loop_ms=float(st.loop_ms), launches=int(st.kernel_launches), voxels=int(np.prod(sim.shape)))
+    sp = sim.sparse_info()
+    res.update(sparse_items=sp["items"], sparse_live_fraction=sp["live_voxels"] / max(sp["voxels"], 1))
     if output is not None:
         lo, virt_shape, out_shape = output
         out_shape = tuple(int(v) for v in out_shape)

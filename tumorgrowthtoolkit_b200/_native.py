@@ -109,6 +109,7 @@ def lib():
     L.tgtk_host_free.argtypes = [ctypes.c_void_p]
     L.tgtk_host_free.restype = None
     L.tgtk_sim_get_tuning.argtypes = [vp, ctypes.POINTER(ctypes.c_int32 * 10)]
+    L.tgtk_sim_sparse_info.argtypes = [vp, ctypes.POINTER(ctypes.c_int64 * 4)]
     L.tgtk_sim_reset.argtypes = [vp]
     L.tgtk_sim_run.argtypes = [vp, ctypes.c_int, ip, ctypes.c_int]
     L.tgtk_sim_sync.argtypes = [vp, ctypes.POINTER(Status)]
@@ -248,6 +249,16 @@ class Sim:
         _check(lib().tgtk_sim_get_tuning(self._h, ctypes.byref(out)))
         return dict(variant=out[0], planes_per_segment=out[1], l2_prefetch_planes=out[2], pdl=bool(out[3]),
                     grid=(out[4], out[5], out[6]), threads=out[7], steps_per_launch=out[8])
+
+    def sparse_info(self):
+        """Sparse launches (include/tgtk_b200.h): work items per launch (0 = dense), voxels in live tiles, voxels."""
+        out = (ctypes.c_int64 * 4)()
+        fn = lib().tgtk_sim_sparse_info
+        if not callable(fn):            # an older build loaded through TGTK_LIB_PATH
+            n = int(np.prod(self.shape))
+            return dict(items=0, live_voxels=n, voxels=n, mask_words=0)
+        _check(fn(self._h, ctypes.byref(out)))
+        return dict(items=int(out[0]), live_voxels=int(out[1]), voxels=int(out[2]), mask_words=int(out[3]))
 
     def run_slab(self, comm, nsteps, halo, owned, prev, nxt):
         _check(lib().tgtk_sim_run_slab(self._h, comm, int(nsteps), int(halo), int(owned), int(prev), int(nxt)))

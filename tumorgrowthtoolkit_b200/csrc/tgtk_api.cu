@@ -19,6 +19,7 @@
 #include "tgtk_kernels_v5.cuh"
 #include "tgtk_kernels_tb.cuh"
 #include "tgtk_kernels_tma.cuh"
+#include "tgtk_kernels_sparse.cuh"
 #include "tgtk_elongate.cuh"
 
 using namespace tgtk;
@@ -119,6 +120,17 @@ struct tgtk_sim {
     // temporal blocking (tgtk_kernels_tb.cuh): two steps per launch where a kernel exists (FK, FK_DTI) and the
     // run is host-scheduled or speculative.  TGTK_TB: 1 on, 0 off, -1 auto (fp64 boxes of more than twice the L2)
     int closed_skip = 1;   // exact per-warp shortcuts of the two-voxel FK / FK_2c kernels (TGTK_CLOSED_SKIP=0: off)
+    // Sparse launches (tgtk_kernels_sparse.cuh): warp tiles outside the tissue that hold no tumour are never loaded, computed
+    // or stored, and the grid is a work list over the rest.  TGTK_SPARSE: 1 on, 0 off, -1 auto (FK_2c boxes beyond L2 with at
+    // least 10 % dead tiles).  Rebuilt by tgtk_sim_run whenever a state or tissue array was uploaded since.
+    int sparse = -1;
+    bool sp_dirty = true, sp_active = false, sp_forbid = false;
+    uint32_t *sp_live = nullptr;
+    int4 *sp_work = nullptr;
+    size_t sp_live_cap = 0, sp_work_cap = 0;
+    int sp_items = 0, sp_nzt = 0, sp_nyt = 0;
+    int64_t sp_live_voxels = 0;      // voxels in live warp tiles
+    double sp_waves = 2.0;           // work items per resident-block slot (TGTK_SP_WAVES)
     int zigzag = 0;        // serpentine sweep of the two-voxel kernels (TGTK_ZIGZAG=1): measured +-1 %, off by default
     int tb = -1;
     int tb_rows = 18;      // thread rows of the two-step kernel's block: 18 (16 output rows, 576 threads) or 10 (8, 320)
@@ -589,6 +601,18 @@ template <typename T> static cudaError_t launch_step(tgtk_sim *s)
         else return launch_v4(s, dti_step_v4<T, 32, 8, 4>, a, s->lx);
         return cudaGetLastError();
     }
+    if (s->sp_active && s->lx > 0 && effective_variant(s) == 4 && s->p.model == TGTK_MODEL_FK_2C) {   // work list over the live tiles
+        const dim3 g = s->grid, b = s->block;
+        s->grid = dim3((unsigned)s->sp_items, 1, 1);
+        s->block = dim3(32, 4, 1);
+        const SparseArgs sp = {s->sp_live, s->sp_work, s->sp_nzt, s->sp_nyt};
+        cudaError_t e;
+        if constexpr (sizeof(T) == 8) e = launch_v4(s, fk2c_step_sp<T, 4>, a, sp);
+        else e = launch_v4(s, fk2c_step_sp<T, 6>, a, sp);
+        s->grid = g;
+        s->block = b;
+        return e;
+    }
     if (s->lx > 0 && effective_variant(s) == 4 && s->p.model == TGTK_MODEL_FK_2C) {   // two voxels per thread
         const int mb = s->minb ? s->minb : ((sizeof(T) == 8) ? 2 : 3);
         if (s->block.x == 16) {
@@ -900,6 +924,143 @@ static int configure_launch(tgtk_sim *s)
     return 0;
 }
 
+// ---- sparse launches: live-tile mask and work list (tgtk_kernels_sparse.cuh) ---------------------------------------
+static bool tb_enabled(const tgtk_sim *s);
+
+static bool sparse_eligible(const tgtk_sim *s)
+{
+    const tgtk_params &p = s->p;
+    if (s->sparse == 0 || s->sp_forbid || s->slab_on || p.model != TGTK_MODEL_FK_2C) return false;
+    if (s->lx <= 0 || effective_variant(s) != 4 || p.X < 8) return false;
+    if ((uint64_t)p.X * (uint64_t)s->sx >= (1ull << 31)) return false;
+    if (s->sparse < 0 && !exceeds_l2(s)) return false;       // auto: where the step streams from HBM
+    return !tb_enabled(s);
+}
+
+static inline int live_warps(uint32_t w) { return ((w & 0xffu) != 0) + ((w & 0xff00u) != 0) + ((w & 0xff0000u) != 0) + ((w >> 24) != 0); }
+
+// The mask of the CURRENT state, the copy of that state into the other ping-pong buffer (a dead tile is never written
+// again: both buffers must hold it), the work list.  Synchronises the stream; once per upload.
+static int build_sparse(tgtk_sim *s)
+{
+    const tgtk_params &p = s->p;
+    const bool was = s->sp_active;
+    s->sp_dirty = false;
+    s->sp_active = false;
+    if (!sparse_eligible(s)) { if (was) drop_graph(s); return 0; }
+    const int nyt = (p.Y + 7) / 8, nzt = (p.Z + 31) / 32;
+    const size_t words = (size_t)p.X * nyt * nzt;
+    if (words > s->sp_live_cap) {
+        if (s->sp_live) CU(sim_free(s, s->sp_live));
+        s->sp_live = nullptr;
+        CU(sim_malloc(s, (void **)(&s->sp_live), words * sizeof(uint32_t)));
+        s->sp_live_cap = words;
+    }
+    const int cur = s->t_enqueued & 1;
+    const size_t bytes = (size_t)p.X * s->sx * s->elem;
+    for (int f = 0; f < s->nfields; ++f)
+        CU(cudaMemcpyAsync(s->state[cur ^ 1][f], s->state[cur][f], bytes, cudaMemcpyDeviceToDevice, s->stream));
+    if (p.dtype == TGTK_F64)
+        sparse_mask_kernel<double, 2><<<(unsigned)words, dim3(32, 4, 1), 0, s->stream>>>(
+            (const double *)s->state[cur][0], (const double *)s->state[cur][1], (const double *)s->coef[0], (const double *)s->coef[1],
+            s->sp_live, p.X, p.Y, p.Z, s->sx, s->sy, nzt, nyt, 0);
+    else
+        sparse_mask_kernel<float, 2><<<(unsigned)words, dim3(32, 4, 1), 0, s->stream>>>(
+            (const float *)s->state[cur][0], (const float *)s->state[cur][1], (const float *)s->coef[0], (const float *)s->coef[1],
+            s->sp_live, p.X, p.Y, p.Z, s->sx, s->sy, nzt, nyt, 0);
+    CU(cudaGetLastError());
+    s->aux_launches += 1;
+    std::vector<uint32_t> live(words);
+    CU(cudaMemcpyAsync(live.data(), s->sp_live, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+
+    // voxels in live warp tiles (the bytes a sparse launch has to move are proportional to it)
+    int64_t live_vox = 0;
+    auto at = [&](int x, int zt, int yt) { return live[((size_t)x * nzt + zt) * nyt + yt]; };
+    for (int x = 0; x < p.X; ++x)
+        for (int zt = 0; zt < nzt; ++zt)
+            for (int yt = 0; yt < nyt; ++yt) {
+                const uint32_t w = at(x, zt, yt);
+                const int zs = std::min(32, p.Z - zt * 32);
+                for (int k = 0; k < 4; ++k)
+                    if ((w >> (8 * k)) & 0xffu) live_vox += (int64_t)zs * std::max(0, std::min(2, p.Y - (yt * 8 + 2 * k)));
+            }
+    s->sp_live_voxels = live_vox;
+    if (s->sparse < 0 && (double)live_vox > 0.9 * (double)s->n) { if (was) drop_graph(s); return 0; }   // nothing to gain
+    if (live_vox == 0) { if (was) drop_graph(s); return 0; }                                             // (and nothing to launch)
+
+    // runs of planes with live tiles per (y tile, z tile) column; a gap of kGap dead planes ends a run
+    struct Run { int yt, zt, x0, x1; double w; };
+    const int kGap = 4;
+    const double kBase = 0.6, kDeadPlane = 0.15;       // relative cost of a block plane: fixed part / one without live warps
+    auto cost = [&](uint32_t w) { return w ? kBase + live_warps(w) : kDeadPlane; };
+    std::vector<Run> runs;
+    double total = 0.0;
+    for (int zt = 0; zt < nzt; ++zt)
+        for (int yt = 0; yt < nyt; ++yt) {
+            int x = 0;
+            while (x < p.X) {
+                while (x < p.X && !at(x, zt, yt)) ++x;
+                if (x >= p.X) break;
+                int x0 = x, last = x;
+                double w = 0.0;
+                for (; x < p.X && x - last <= kGap; ++x)
+                    if (at(x, zt, yt)) last = x;
+                for (int q = x0; q <= last; ++q) w += cost(at(q, zt, yt));
+                runs.push_back({yt, zt, x0, last + 1, w});
+                total += w;
+                x = last + 1;
+            }
+        }
+    int per_sm = 4, sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+    const void *fn = (p.dtype == TGTK_F64) ? (const void *)fk2c_step_sp<double, 4> : (const void *)fk2c_step_sp<float, 6>;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    const double target = std::max(total / ((double)sms * per_sm * s->sp_waves), 4.0 * (kBase + 4.0));   // at least ~4 full planes
+    std::vector<Run> items;
+    for (const Run &r : runs) {
+        const int pieces = std::max(1, std::min(r.x1 - r.x0, (int)std::lround(r.w / target)));
+        const double each = r.w / pieces;
+        int x0 = r.x0;
+        double acc = 0.0, cut = each;
+        for (int q = r.x0, k = 1; q < r.x1; ++q) {
+            acc += cost(at(q, r.zt, r.yt));
+            if ((k < pieces && acc >= cut - 1e-9 && q + 1 < r.x1) || q + 1 == r.x1) {
+                double w = 0.0;
+                for (int t = x0; t <= q; ++t) w += cost(at(t, r.zt, r.yt));
+                items.push_back({r.yt, r.zt, x0, q + 1, w});
+                x0 = q + 1;
+                ++k;
+                cut = each * k;
+            }
+        }
+    }
+    std::stable_sort(items.begin(), items.end(), [](const Run &a, const Run &b) { return a.w > b.w; });   // longest first
+    std::vector<int4> work(items.size());
+    for (size_t i = 0; i < items.size(); ++i) work[i] = make_int4(items[i].yt, items[i].zt, items[i].x0, items[i].x1);
+    if (work.size() > s->sp_work_cap) {
+        if (s->sp_work) CU(sim_free(s, s->sp_work));
+        s->sp_work = nullptr;
+        CU(sim_malloc(s, (void **)(&s->sp_work), work.size() * sizeof(int4)));
+        s->sp_work_cap = work.size();
+    }
+    CU(cudaMemcpyAsync(s->sp_work, work.data(), work.size() * sizeof(int4), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    s->sp_items = (int)work.size();
+    s->sp_nzt = nzt;
+    s->sp_nyt = nyt;
+    if ((unsigned)s->sp_items > s->partials_cap) {
+        if (s->partials) CU(sim_free(s, s->partials));
+        s->partials = nullptr;
+        CU(sim_malloc(s, (void **)(&s->partials), sizeof(double) * 2 * s->sp_items * kGraphSteps));
+        s->partials_cap = (unsigned)s->sp_items;
+        s->ring_stride = 2 * s->partials_cap;
+    }
+    s->sp_active = true;
+    drop_graph(s);
+    return 0;
+}
+
 static int ensure_volumes(tgtk_sim *s, int need)
 {
     if (need <= s->volumes_cap) return 0;
@@ -1001,7 +1162,8 @@ static cudaError_t launch_chunk_finish(tgtk_sim *s, int count)
     const tgtk_params &p = s->p;
     const int spec = (s->spec && !s->replaying) ? 1 : 0;
     ++s->aux_launches;
-    chunk_finish_kernel<<<count, 256, 0, s->stream>>>(s->ctrl, s->partials, s->volumes, s->volumes_cap, s->nblocks, s->nfields,
+    chunk_finish_kernel<<<count, 256, 0, s->stream>>>(s->ctrl, s->partials, s->volumes, s->volumes_cap,
+                                                   s->sp_active ? (unsigned)s->sp_items : s->nblocks, s->nfields,
                                                    count, p.h[0] * p.h[1] * p.h[2], 1.0, spec,
                                                    p.stopping_volume, p.small_volume, s->ring_stride, s->tb_nblocks,
                                                    s->chunk_tb_mask, s->slab_on ? s->chunkvol : nullptr);
@@ -1279,6 +1441,8 @@ int tgtk_sim_create_ex(tgtk_sim **out, const tgtk_params *params, int device, vo
     if (const char *v = getenv("TGTK_TB")) s->tb = atoi(v);
     if (const char *v = getenv("TGTK_ZIGZAG")) s->zigzag = atoi(v) != 0;
     if (const char *v = getenv("TGTK_CLOSED_SKIP")) s->closed_skip = atoi(v) != 0;
+    if (const char *v = getenv("TGTK_SPARSE")) s->sparse = atoi(v);
+    if (const char *v = getenv("TGTK_SP_WAVES")) s->sp_waves = std::max(0.25, atof(v));
     if (const char *v = getenv("TGTK_TB_ROWS")) s->tb_rows = atoi(v);
     if (const char *v = getenv("TGTK_TMA_ROWS")) s->tma_rows = (atoi(v) == 8) ? 8 : 4;
     if (const char *v = getenv("TGTK_TMA_STAGES")) s->tma_stages = (atoi(v) == 2) ? 2 : (atoi(v) == 4) ? 4 : 3;
@@ -1324,6 +1488,8 @@ void tgtk_sim_destroy(tgtk_sim *s)
     for (int c = 0; c < 12; ++c) sim_free(s, s->coef[c]);
     for (void *q : s->snaps) sim_free(s, q);
     sim_free(s, s->stage);
+    sim_free(s, s->sp_live);
+    sim_free(s, s->sp_work);
     sim_free(s, s->resample_out);
     for (int f = 0; f < 3; ++f) sim_free(s, s->resample_async[f]);
     sim_free(s, s->seg_out);
@@ -1370,7 +1536,20 @@ int tgtk_sim_get_tuning(tgtk_sim *s, int32_t out[10])
     out[4] = (int32_t)s->grid.x; out[5] = (int32_t)s->grid.y; out[6] = (int32_t)s->grid.z;
     out[7] = (int32_t)(s->block.x * s->block.y * s->block.z);
     out[8] = tb_enabled(s) ? 2 : 1;
-    out[9] = 0;
+    out[9] = s->sp_active ? s->sp_items : 0;       // work items of a sparse launch (0: dense grid)
+    return 0;
+}
+
+int tgtk_sim_sparse_info(tgtk_sim *s, int64_t out[4])
+{
+    if (!s || !out) return fail("tgtk_sim_sparse_info", "null argument");
+    if (!s->prepared) return fail("tgtk_sim_sparse_info", "call tgtk_sim_prepare first");
+    CU(cudaSetDevice(s->device));
+    if ((s->sp_dirty || s->sp_active != sparse_eligible(s)) && (s->sp_active || sparse_eligible(s)) && build_sparse(s)) return 1;
+    out[0] = s->sp_active ? s->sp_items : 0;
+    out[1] = s->sp_active ? s->sp_live_voxels : (int64_t)s->n;
+    out[2] = (int64_t)s->n;
+    out[3] = s->sp_active ? (int64_t)s->p.X * s->sp_nzt * s->sp_nyt : 0;
     return 0;
 }
 
@@ -1390,6 +1569,7 @@ int tgtk_sim_buffer_ptr(tgtk_sim *s, int field, int which, unsigned long long *p
     if (!s || !ptr) return fail("tgtk_sim_buffer_ptr", "null argument");
     if (field < 0 || field >= s->nfields || which < 0 || which > 1) return fail("tgtk_sim_buffer_ptr", "no such buffer");
     *ptr = (unsigned long long)(uintptr_t)s->state[which][field];
+    s->sp_forbid = true;       // the caller writes the buffers behind the library's back (halo exchanges): every tile is stored
     return 0;
 }
 
@@ -1408,9 +1588,11 @@ int tgtk_sim_upload(tgtk_sim *s, int field, const double *host, const int64_t st
         if (copy_host_stage(s, const_cast<double *>(host), strides, true)) return 1;
         CU(cudaMemcpyAsync(*dst, s->stage, s->n * 8, cudaMemcpyDeviceToDevice, s->stream));
         s->prepared = false;
+        s->sp_dirty = true;
         return 0;
     }
     const int cur = s->t_enqueued & 1;
+    s->sp_dirty = true;
     void *dst = field_ptr(s, field, cur);
     if (!dst) return fail("tgtk_sim_upload", "field not present in this model");
     if (field >= TGTK_FIELD_COEF0 && p.model != TGTK_MODEL_DTI && p.model != TGTK_MODEL_COEF6 &&
@@ -1557,6 +1739,7 @@ int tgtk_sim_prepare(tgtk_sim *s)
         CU(cudaMemcpyAsync(s->initial[f], s->state[cur][f], bytes, cudaMemcpyDeviceToDevice, s->stream));
     }
     s->prepared = true;
+    s->sp_dirty = true;
     return 0;
 }
 
@@ -1587,6 +1770,7 @@ int tgtk_sim_run(tgtk_sim *s, int nsteps, const int32_t *record_steps, int nreco
     if (nsteps < 0) return fail("tgtk_sim_run", "negative step count");
     CU(cudaSetDevice(s->device));
     if (s->pads_dirty && zpair_variant(s) && refresh_pads(s)) return 1;
+    if ((s->sp_dirty || s->sp_active != sparse_eligible(s)) && (s->sp_active || sparse_eligible(s)) && build_sparse(s)) return 1;
     if (ensure_volumes(s, s->t_enqueued + nsteps)) return 1;
     s->ctrl_valid = false;
     const size_t bytes = (size_t)s->p.X * s->sx * s->elem;
