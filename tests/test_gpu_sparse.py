@@ -64,7 +64,7 @@ def test_fk2c_sparse_equals_dense(shape, precision):
         assert len(a["snapshots"][k]) == len(rec)
         for p, q in zip(a["snapshots"][k], b["snapshots"][k]):
             assert np.array_equal(p, q)
-    assert a["volume"] == b["volume"]
+    assert abs(a["volume"] - b["volume"]) <= 1e-12 * abs(b["volume"])      # per-block partial sums: another grid, another order
     assert a["state"]["N"].max() > 0.1
 
 
