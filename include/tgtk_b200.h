@@ -135,8 +135,12 @@ int tgtk_sim_get_tuning(tgtk_sim *sim, int32_t out[10]);
  * the 2 x 32 voxel tiles that consist of such voxels only are neither loaded, computed nor stored, and the launch grid is a
  * work list over the rest: same results bit for bit, proportionally less HBM traffic.  Decided from the current state the
  * next time tgtk_sim_run is called after an upload (or by this call).  out[0] work items per launch (0: dense launches),
- * out[1] voxels in live tiles, out[2] voxels of the box, out[3] words of the tile mask. */
+ * out[1] voxels in live tiles, out[2] voxels of the box, out[3] resident blocks per SM of the sparse kernel. */
 int tgtk_sim_sparse_info(tgtk_sim *sim, int64_t out[4]);
+/* Diagnostic (tools/sparse_trace.py): runs one more step and reports, per work item i, out[4*i + 0..2] = nanoseconds from the
+ * first block's start to this block's start / to the end of its prologue / to the end of its plane loop, out[4*i + 3] = the SM
+ * it ran on; planes[2*i + 0..1] = its plane range (may be NULL).  cap: items the arrays hold (>= tgtk_sim_sparse_info out[0]). */
+int tgtk_sim_sparse_trace(tgtk_sim *sim, int64_t *out, int32_t *planes, int cap);
 
 /* Slab decomposition support.  set_sum_range: only planes [x0, x1) of axis 0 count towards the
  * volume (a rank's owned planes; its ghost planes are stepped but not summed).  buffer_ptr: device

@@ -136,3 +136,43 @@ def test_fk2c_sparse_reset_and_new_state():
             assert np.array_equal(sim.download(f), ref.download(f)), k
     finally:
         sim.close(); ref.close()
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("shape", [(40, 48, 70), (33, 41, 37)])
+def test_fk_sparse_equals_dense(shape, precision):
+    from tumorgrowthtoolkit_b200 import _loop
+    wm, gm, u0, _ = _problem(shape)
+    rec = np.arange(0, 90, 17)
+    args = (u0, wm, gm, 0.1, 1.0, 10.0, 0.2, 0.03, 1.0, 1.0, 1.0, 90)
+    with _env(TGTK_SPARSE=1, TGTK_VARIANT=4):
+        a = _loop.fk_loop(*args, precision=precision, record_steps=rec)
+    with _env(TGTK_SPARSE=0, TGTK_VARIANT=4):
+        b = _loop.fk_loop(*args, precision=precision, record_steps=rec)
+    assert a["sparse_items"] > 0 and b["sparse_items"] == 0
+    assert np.array_equal(a["state"], b["state"])
+    for p, q in zip(a["snapshots"], b["snapshots"]):
+        assert np.array_equal(p, q)
+    assert abs(a["volume"] - b["volume"]) <= 1e-12 * abs(b["volume"])
+    assert (a["state"] > 0).sum() > 2 * (u0 > 0).sum()          # the tumour spread into tiles that held none
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("shape", [(40, 48, 70), (33, 41, 37)])
+def test_dti_sparse_equals_dense(shape, precision):
+    from tumorgrowthtoolkit_b200 import _loop
+    wm, gm, u0, _ = _problem(shape)
+    rng = np.random.default_rng(5)
+    rgb = rng.uniform(0.05, 1.0, shape + (3,)) * (wm + gm >= 0.1)[..., None]
+    u0 = u0 * (wm + gm >= 0.1)
+    args = (u0, rgb, 1.0, 0.2, 0.03, 1.0, 1.0, 1.0, 90)
+    out = []
+    for sparse in (1, 0):
+        with _env(TGTK_SPARSE=sparse, TGTK_VARIANT=4, TGTK_TB=0):
+            out.append(_loop.dti_loop(*args, precision=precision, record_steps=np.arange(0, 90, 17)))
+    a, b = out
+    assert a["sparse_items"] > 0 and b["sparse_items"] == 0
+    assert np.array_equal(a["state"], b["state"])
+    for p, q in zip(a["snapshots"], b["snapshots"]):
+        assert np.array_equal(p, q)
+    assert abs(a["volume"] - b["volume"]) <= 1e-12 * abs(b["volume"])

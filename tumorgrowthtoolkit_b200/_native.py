@@ -110,6 +110,7 @@ def lib():
     L.tgtk_host_free.restype = None
     L.tgtk_sim_get_tuning.argtypes = [vp, ctypes.POINTER(ctypes.c_int32 * 10)]
     L.tgtk_sim_sparse_info.argtypes = [vp, ctypes.POINTER(ctypes.c_int64 * 4)]
+    L.tgtk_sim_sparse_trace.argtypes = [vp, ctypes.POINTER(ctypes.c_int64), ip, ctypes.c_int]
     L.tgtk_sim_reset.argtypes = [vp]
     L.tgtk_sim_run.argtypes = [vp, ctypes.c_int, ip, ctypes.c_int]
     L.tgtk_sim_sync.argtypes = [vp, ctypes.POINTER(Status)]
@@ -256,9 +257,18 @@ class Sim:
         fn = lib().tgtk_sim_sparse_info
         if not callable(fn):            # an older build loaded through TGTK_LIB_PATH
             n = int(np.prod(self.shape))
-            return dict(items=0, live_voxels=n, voxels=n, mask_words=0)
+            return dict(items=0, live_voxels=n, voxels=n, blocks_per_sm=0)
         _check(fn(self._h, ctypes.byref(out)))
-        return dict(items=int(out[0]), live_voxels=int(out[1]), voxels=int(out[2]), mask_words=int(out[3]))
+        return dict(items=int(out[0]), live_voxels=int(out[1]), voxels=int(out[2]), blocks_per_sm=int(out[3]))
+
+    def sparse_trace(self):
+        """One more step with per-item timestamps: (items, 4) int64 [start ns, prologue end ns, loop end ns, SM], (items, 2) planes."""
+        n = self.sparse_info()["items"]
+        out = np.zeros((n, 4), dtype=np.int64)
+        planes = np.zeros((n, 2), dtype=np.int32)
+        _check(lib().tgtk_sim_sparse_trace(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                           planes.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), n))
+        return out, planes
 
     def run_slab(self, comm, nsteps, halo, owned, prev, nxt):
         _check(lib().tgtk_sim_run_slab(self._h, comm, int(nsteps), int(halo), int(owned), int(prev), int(nxt)))

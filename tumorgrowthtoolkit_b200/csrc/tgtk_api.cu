@@ -130,7 +130,13 @@ struct tgtk_sim {
     size_t sp_live_cap = 0, sp_work_cap = 0;
     int sp_items = 0, sp_nzt = 0, sp_nyt = 0;
     int64_t sp_live_voxels = 0;      // voxels in live warp tiles
-    double sp_waves = 2.0;           // work items per resident-block slot (TGTK_SP_WAVES)
+    double sp_waves = 1.0;           // work items per resident-block slot (TGTK_SP_WAVES); measured best: one (every item pays a 3 us prologue)
+    int sp_carveout = -1;
+    int64_t sp_min_voxels = 1 << 18;  // TGTK_SPARSE_MIN_VOXELS
+    int sp_ahead = 0;                // TGTK_SP_AHEAD: prologue prefetch for a later item (measured: no gain), -1 = resident blocks of the device
+    double sp_split = 0.5;           // TGTK_SP_SPLIT: share of a slot's work in its first item
+    unsigned long long *sp_trace = nullptr;      // tgtk_sim_sparse_trace: per-item timestamps of the next launches
+    int sp_async = 0, sp_minb = 4, sp_per_sm = 0;   // TGTK_SP_ASYNC=2: own voxels staged by cp.async two planes ahead; TGTK_SP_MINB
     int zigzag = 0;        // serpentine sweep of the two-voxel kernels (TGTK_ZIGZAG=1): measured +-1 %, off by default
     int tb = -1;
     int tb_rows = 18;      // thread rows of the two-step kernel's block: 18 (16 output rows, 576 threads) or 10 (8, 320)
@@ -409,7 +415,7 @@ static int effective_variant(const tgtk_sim *s)
     if (s->slab_on) return 4;              // the in-kernel halo push lives in the two-voxel kernels
     if (s->variant == 0) {
         if (!has_v5(s)) return 4;
-        if (s->p.model == TGTK_MODEL_DTI) return 6;
+        if (s->p.model == TGTK_MODEL_DTI) return s->sp_active ? 4 : 6;      // sparse launches exist for the two-voxel kernels only, and win
         // FK / FK_2c fp32: the two-voxel kernels.  Round 2 moved the z-pair kernels' left / right neighbours to warp shuffles,
         // which makes them 13 % faster than the two-voxel FK kernel on all-tissue random boxes -- but on the atlas, where 60 %
         // of the box is background, the two-voxel kernel's closed-warp shortcut wins (281 vs 267 GLUPS): they stay opt-in
@@ -589,6 +595,26 @@ template <typename T> static cudaError_t launch_step(tgtk_sim *s)
         default: break;
         }
     }
+    if (s->sp_active && s->lx > 0 && effective_variant(s) == 4) {   // work list over the live tiles
+        const dim3 g = s->grid, b = s->block;
+        s->grid = dim3((unsigned)s->sp_items, 1, 1);
+        s->block = dim3(32, 4, 1);
+        const SparseArgs sp = {s->sp_live, s->sp_work, s->sp_ahead, s->sp_nzt, s->sp_nyt, s->sp_trace};
+        cudaError_t e;
+        if (s->p.model == TGTK_MODEL_FK) e = launch_v4(s, fk_step_sp<T, 8>, a, sp);
+        else if (s->p.model == TGTK_MODEL_DTI) e = launch_v4(s, dti_step_sp<T, 8>, a, sp);
+        else if constexpr (sizeof(T) == 8) {
+            if (s->sp_async == 2 && s->sp_minb == 5) e = launch_v4(s, fk2c_step_spa<T, 5, 2>, a, sp);
+            else if (s->sp_async == 2) e = launch_v4(s, fk2c_step_spa<T, 4, 2>, a, sp);
+            else e = launch_v4(s, fk2c_step_sp<T, 4>, a, sp);
+        } else {
+            if (s->sp_async == 2) e = launch_v4(s, fk2c_step_spa<T, 6, 2>, a, sp);
+            else e = launch_v4(s, fk2c_step_sp<T, 6>, a, sp);
+        }
+        s->grid = g;
+        s->block = b;
+        return e;
+    }
     if (s->lx > 0 && effective_variant(s) == 4 && s->p.model == TGTK_MODEL_FK) {
         if (s->block.x == 16) return launch_v4(s, fk_step_v4<T, 16, 8, 8>, a, s->lx);
         else if (s->block.y == 4) return launch_v4(s, fk_step_v4<T, 32, 4, 8>, a, s->lx);
@@ -600,18 +626,6 @@ template <typename T> static cudaError_t launch_step(tgtk_sim *s)
         else if (s->block.y == 4) return launch_v4(s, dti_step_v4<T, 32, 4, 8>, a, s->lx);
         else return launch_v4(s, dti_step_v4<T, 32, 8, 4>, a, s->lx);
         return cudaGetLastError();
-    }
-    if (s->sp_active && s->lx > 0 && effective_variant(s) == 4 && s->p.model == TGTK_MODEL_FK_2C) {   // work list over the live tiles
-        const dim3 g = s->grid, b = s->block;
-        s->grid = dim3((unsigned)s->sp_items, 1, 1);
-        s->block = dim3(32, 4, 1);
-        const SparseArgs sp = {s->sp_live, s->sp_work, s->sp_nzt, s->sp_nyt};
-        cudaError_t e;
-        if constexpr (sizeof(T) == 8) e = launch_v4(s, fk2c_step_sp<T, 4>, a, sp);
-        else e = launch_v4(s, fk2c_step_sp<T, 6>, a, sp);
-        s->grid = g;
-        s->block = b;
-        return e;
     }
     if (s->lx > 0 && effective_variant(s) == 4 && s->p.model == TGTK_MODEL_FK_2C) {   // two voxels per thread
         const int mb = s->minb ? s->minb : ((sizeof(T) == 8) ? 2 : 3);
@@ -930,10 +944,12 @@ static bool tb_enabled(const tgtk_sim *s);
 static bool sparse_eligible(const tgtk_sim *s)
 {
     const tgtk_params &p = s->p;
-    if (s->sparse == 0 || s->sp_forbid || s->slab_on || p.model != TGTK_MODEL_FK_2C) return false;
-    if (s->lx <= 0 || effective_variant(s) != 4 || p.X < 8) return false;
+    if (s->sparse == 0 || s->sp_forbid || s->slab_on) return false;
+    if (p.model != TGTK_MODEL_FK_2C && p.model != TGTK_MODEL_FK && p.model != TGTK_MODEL_DTI) return false;
+    const bool dti32_auto = s->variant == 0 && p.dtype == TGTK_F32 && p.model == TGTK_MODEL_DTI;      // runs the z-pair kernels unless sparse
+    if (s->lx <= 0 || (!dti32_auto && effective_variant(s) != 4) || p.X < 8) return false;
     if ((uint64_t)p.X * (uint64_t)s->sx >= (1ull << 31)) return false;
-    if (s->sparse < 0 && !exceeds_l2(s)) return false;       // auto: where the step streams from HBM
+    if (s->sparse < 0 && s->n < (size_t)s->sp_min_voxels) return false;      // auto: not for boxes whose loop is a few launch latencies long
     return !tb_enabled(s);
 }
 
@@ -941,7 +957,7 @@ static inline int live_warps(uint32_t w) { return ((w & 0xffu) != 0) + ((w & 0xf
 
 // The mask of the CURRENT state, the copy of that state into the other ping-pong buffer (a dead tile is never written
 // again: both buffers must hold it), the work list.  Synchronises the stream; once per upload.
-static int build_sparse(tgtk_sim *s)
+static int build_sparse_inner(tgtk_sim *s)
 {
     const tgtk_params &p = s->p;
     const bool was = s->sp_active;
@@ -960,14 +976,15 @@ static int build_sparse(tgtk_sim *s)
     const size_t bytes = (size_t)p.X * s->sx * s->elem;
     for (int f = 0; f < s->nfields; ++f)
         CU(cudaMemcpyAsync(s->state[cur ^ 1][f], s->state[cur][f], bytes, cudaMemcpyDeviceToDevice, s->stream));
+    const int mode = (p.model == TGTK_MODEL_FK_2C) ? 0 : (p.model == TGTK_MODEL_FK) ? 1 : 2;
     if (p.dtype == TGTK_F64)
         sparse_mask_kernel<double, 2><<<(unsigned)words, dim3(32, 4, 1), 0, s->stream>>>(
             (const double *)s->state[cur][0], (const double *)s->state[cur][1], (const double *)s->coef[0], (const double *)s->coef[1],
-            s->sp_live, p.X, p.Y, p.Z, s->sx, s->sy, nzt, nyt, 0);
+            (const double *)s->coef[2], s->sp_live, p.X, p.Y, p.Z, s->sx, s->sy, nzt, nyt, mode);
     else
         sparse_mask_kernel<float, 2><<<(unsigned)words, dim3(32, 4, 1), 0, s->stream>>>(
             (const float *)s->state[cur][0], (const float *)s->state[cur][1], (const float *)s->coef[0], (const float *)s->coef[1],
-            s->sp_live, p.X, p.Y, p.Z, s->sx, s->sy, nzt, nyt, 0);
+            (const float *)s->coef[2], s->sp_live, p.X, p.Y, p.Z, s->sx, s->sy, nzt, nyt, mode);
     CU(cudaGetLastError());
     s->aux_launches += 1;
     std::vector<uint32_t> live(words);
@@ -992,8 +1009,12 @@ static int build_sparse(tgtk_sim *s)
     // runs of planes with live tiles per (y tile, z tile) column; a gap of kGap dead planes ends a run
     struct Run { int yt, zt, x0, x1; double w; };
     const int kGap = 4;
-    const double kBase = 0.6, kDeadPlane = 0.15;       // relative cost of a block plane: fixed part / one without live warps
-    auto cost = [&](uint32_t w) { return w ? kBase + live_warps(w) : kDeadPlane; };
+    // Relative cost of a block plane.  Measured (tools/sparse_trace.py): a plane takes a block 1.5-1.9 us whether one or four
+    // of its warps are live -- the barrier makes the block as slow as its slowest warp -- and a plane without live warps a
+    // fraction of that.  TGTK_SP_COST="base:per_warp:dead".
+    double kBase = 3.4, kWarp = 0.15, kDeadPlane = 0.4;
+    if (const char *v = getenv("TGTK_SP_COST")) sscanf(v, "%lf:%lf:%lf", &kBase, &kWarp, &kDeadPlane);
+    auto cost = [&](uint32_t w) { return w ? kBase + kWarp * live_warps(w) : kDeadPlane; };
     std::vector<Run> runs;
     double total = 0.0;
     for (int zt = 0; zt < nzt; ++zt)
@@ -1014,30 +1035,51 @@ static int build_sparse(tgtk_sim *s)
         }
     int per_sm = 4, sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
-    const void *fn = (p.dtype == TGTK_F64) ? (const void *)fk2c_step_sp<double, 4> : (const void *)fk2c_step_sp<float, 6>;
+    const bool f64 = (p.dtype == TGTK_F64);
+    const void *fn;
+    if (p.model == TGTK_MODEL_FK) fn = f64 ? (const void *)fk_step_sp<double, 8> : (const void *)fk_step_sp<float, 8>;
+    else if (p.model == TGTK_MODEL_DTI) fn = f64 ? (const void *)dti_step_sp<double, 8> : (const void *)dti_step_sp<float, 8>;
+    else
+        fn = f64 ? (s->sp_async == 2 ? (s->sp_minb == 5 ? (const void *)fk2c_step_spa<double, 5, 2> : (const void *)fk2c_step_spa<double, 4, 2>)
+                                     : (const void *)fk2c_step_sp<double, 4>)
+                 : (s->sp_async == 2 ? (const void *)fk2c_step_spa<float, 6, 2> : (const void *)fk2c_step_sp<float, 6>);
+    if (s->sp_carveout >= 0) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, s->sp_carveout);   // TGTK_SP_CARVEOUT: experiments
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
-    const double target = std::max(total / ((double)sms * per_sm * s->sp_waves), 4.0 * (kBase + 4.0));   // at least ~4 full planes
+    s->sp_per_sm = per_sm;
+    if (s->sp_ahead < 0) s->sp_ahead = sms * per_sm;
+    // a slot's share of the work, cut into `waves` items; two items per slot: the first one takes `split` of it, so that
+    // the blocks of the second round are the short ones and the launch ends evenly
+    const double floor_w = 4.0 * (kBase + 4.0);       // at least ~4 full planes per item: every item pays a prologue
+    const double share = total / ((double)sms * per_sm);
+    const bool two = std::fabs(s->sp_waves - 2.0) < 1e-9;
+    const double tgt[2] = {std::max(two ? share * s->sp_split : share / s->sp_waves, floor_w),
+                           std::max(two ? share * (1.0 - s->sp_split) : share / s->sp_waves, floor_w)};
     std::vector<Run> items;
+    int turn = 0;
     for (const Run &r : runs) {
-        const int pieces = std::max(1, std::min(r.x1 - r.x0, (int)std::lround(r.w / target)));
-        const double each = r.w / pieces;
         int x0 = r.x0;
-        double acc = 0.0, cut = each;
-        for (int q = r.x0, k = 1; q < r.x1; ++q) {
-            acc += cost(at(q, r.zt, r.yt));
-            if ((k < pieces && acc >= cut - 1e-9 && q + 1 < r.x1) || q + 1 == r.x1) {
-                double w = 0.0;
-                for (int t = x0; t <= q; ++t) w += cost(at(t, r.zt, r.yt));
-                items.push_back({r.yt, r.zt, x0, q + 1, w});
+        double acc = 0.0, left = r.w;
+        for (int q = r.x0; q < r.x1; ++q) {
+            const double c = cost(at(q, r.zt, r.yt));
+            acc += c;
+            left -= c;
+            const bool last = (q + 1 == r.x1);
+            // cut when the item has reached its size and what is left of the run is worth an item of its own
+            if (last || (acc >= tgt[turn] - 1e-9 && left >= 0.5 * std::min(tgt[0], tgt[1]))) {
+                items.push_back({r.yt, r.zt, x0, q + 1, acc});
                 x0 = q + 1;
-                ++k;
-                cut = each * k;
+                acc = 0.0;
+                turn ^= 1;
             }
         }
     }
     std::stable_sort(items.begin(), items.end(), [](const Run &a, const Run &b) { return a.w > b.w; });   // longest first
-    std::vector<int4> work(items.size());
-    for (size_t i = 0; i < items.size(); ++i) work[i] = make_int4(items[i].yt, items[i].zt, items[i].x0, items[i].x1);
+    std::vector<int4> work(2 * items.size());
+    auto word = [&](const Run &r, int d) { return (int)at((r.x0 + d) % p.X, r.zt, r.yt); };
+    for (size_t i = 0; i < items.size(); ++i) {
+        work[2 * i] = make_int4(items[i].yt, items[i].zt, items[i].x0, items[i].x1);
+        work[2 * i + 1] = make_int4(word(items[i], 0), word(items[i], 1), word(items[i], 2), word(items[i], 3));
+    }
     if (work.size() > s->sp_work_cap) {
         if (s->sp_work) CU(sim_free(s, s->sp_work));
         s->sp_work = nullptr;
@@ -1046,7 +1088,7 @@ static int build_sparse(tgtk_sim *s)
     }
     CU(cudaMemcpyAsync(s->sp_work, work.data(), work.size() * sizeof(int4), cudaMemcpyHostToDevice, s->stream));
     CU(cudaStreamSynchronize(s->stream));
-    s->sp_items = (int)work.size();
+    s->sp_items = (int)items.size();
     s->sp_nzt = nzt;
     s->sp_nyt = nyt;
     if ((unsigned)s->sp_items > s->partials_cap) {
@@ -1058,6 +1100,18 @@ static int build_sparse(tgtk_sim *s)
     }
     s->sp_active = true;
     drop_graph(s);
+    return 0;
+}
+
+static int build_sparse(tgtk_sim *s)
+{
+    const bool was = s->sp_active;
+    const int v0 = effective_variant(s);
+    if (build_sparse_inner(s)) return 1;
+    if (s->sp_active != was && effective_variant(s) != v0) {      // FK_DTI fp32: the kernel family follows the mode
+        if (configure_launch(s)) return 1;
+        if (s->sp_active && (unsigned)s->sp_items > s->partials_cap) return fail("sparse", "partial-sum ring too small");
+    }
     return 0;
 }
 
@@ -1416,6 +1470,12 @@ int tgtk_sim_create_ex(tgtk_sim **out, const tgtk_params *params, int device, vo
         const bool even64 = e ? atoi(e) != 0 : (v && atoi(v) == 7);
         s->sy = p.Z + ((p.dtype == TGTK_F32 || even64) ? (p.Z & 1) : 0);
         if (even64 && p.dtype == TGTK_F32) s->sy = (p.Z + 3) / 4 * 4;      // 16-byte rows in fp32 too
+        // TGTK_PITCH_ALIGN=bytes: rows start on a multiple of that many bytes (128: a warp's 32-voxel row segment then touches
+        // 2 lines in fp64 / 1 in fp32 instead of 3 / 2 -- the marching kernels are bound by L1 wavefronts)
+        if (const char *pa = getenv("TGTK_PITCH_ALIGN")) {
+            const int64_t el = std::max<int64_t>(1, atoi(pa) / (int64_t)s->elem);
+            s->sy = (s->sy + el - 1) / el * el;
+        }
     }
     s->sx = (int64_t)p.Y * s->sy;
     s->nfields = (p.model == TGTK_MODEL_FK_2C || p.model == TGTK_MODEL_FK2C_COEF12) ? 3 : 1;
@@ -1443,6 +1503,12 @@ int tgtk_sim_create_ex(tgtk_sim **out, const tgtk_params *params, int device, vo
     if (const char *v = getenv("TGTK_CLOSED_SKIP")) s->closed_skip = atoi(v) != 0;
     if (const char *v = getenv("TGTK_SPARSE")) s->sparse = atoi(v);
     if (const char *v = getenv("TGTK_SP_WAVES")) s->sp_waves = std::max(0.25, atof(v));
+    if (const char *v = getenv("TGTK_SP_ASYNC")) s->sp_async = atoi(v);
+    if (const char *v = getenv("TGTK_SPARSE_MIN_VOXELS")) s->sp_min_voxels = atoll(v);
+    if (const char *v = getenv("TGTK_SP_AHEAD")) s->sp_ahead = atoi(v);
+    if (const char *v = getenv("TGTK_SP_SPLIT")) s->sp_split = std::min(0.9, std::max(0.1, atof(v)));
+    if (const char *v = getenv("TGTK_SP_CARVEOUT")) s->sp_carveout = atoi(v);
+    if (const char *v = getenv("TGTK_SP_MINB")) s->sp_minb = atoi(v);
     if (const char *v = getenv("TGTK_TB_ROWS")) s->tb_rows = atoi(v);
     if (const char *v = getenv("TGTK_TMA_ROWS")) s->tma_rows = (atoi(v) == 8) ? 8 : 4;
     if (const char *v = getenv("TGTK_TMA_STAGES")) s->tma_stages = (atoi(v) == 2) ? 2 : (atoi(v) == 4) ? 4 : 3;
@@ -1549,7 +1615,50 @@ int tgtk_sim_sparse_info(tgtk_sim *s, int64_t out[4])
     out[0] = s->sp_active ? s->sp_items : 0;
     out[1] = s->sp_active ? s->sp_live_voxels : (int64_t)s->n;
     out[2] = (int64_t)s->n;
-    out[3] = s->sp_active ? (int64_t)s->p.X * s->sp_nzt * s->sp_nyt : 0;
+    out[3] = s->sp_active ? (int64_t)s->sp_per_sm : 0;      // resident blocks per SM of the sparse kernel
+    return 0;
+}
+
+/* diagnostic: run ONE more step with per-item timestamps (nanoseconds of the global timer, relative to the earliest block
+ * start): out[4*i + 0..3] = block start, end of the prologue, end of the plane loop, SM id; plus the item's planes in
+ * planes[2*i + 0..1] */
+int tgtk_sim_sparse_trace(tgtk_sim *s, int64_t *out, int32_t *planes, int cap)
+{
+    if (!s || !out) return fail("tgtk_sim_sparse_trace", "null argument");
+    if (!s->sp_active) return fail("tgtk_sim_sparse_trace", "the simulation does not run sparse launches");
+    if (cap < s->sp_items) return fail("tgtk_sim_sparse_trace", "output too small");
+    CU(cudaSetDevice(s->device));
+    const size_t bytes = (size_t)s->sp_items * 4 * sizeof(unsigned long long);
+    const size_t bytes_all = bytes + (size_t)s->sp_items * 32 * sizeof(unsigned long long);     // + the phase counters of a -DTGTK_SP_PHASES build
+    CU(sim_malloc(s, (void **)(&s->sp_trace), bytes_all));
+    CU(cudaMemsetAsync(s->sp_trace, 0, bytes_all, s->stream));
+    const bool g = s->use_graph;
+    s->use_graph = false;
+    int rc = tgtk_sim_run(s, 1, nullptr, 0);
+    s->use_graph = g;
+    std::vector<unsigned long long> t((size_t)s->sp_items * 4);
+    std::vector<int4> w2((size_t)s->sp_items * 2);
+    if (!rc) {
+        CU(cudaMemcpyAsync(t.data(), s->sp_trace, bytes, cudaMemcpyDeviceToHost, s->stream));
+        if (const char *v = getenv("TGTK_SP_PHASES_OUT")) {      // diagnostic build: raw phase counters to a file
+            std::vector<unsigned long long> ph((size_t)s->sp_items * 32);
+            CU(cudaMemcpyAsync(ph.data(), (char *)s->sp_trace + bytes, ph.size() * 8, cudaMemcpyDeviceToHost, s->stream));
+            CU(cudaStreamSynchronize(s->stream));
+            if (FILE *f = fopen(v, "wb")) { fwrite(ph.data(), 8, ph.size(), f); fclose(f); }
+        }
+        CU(cudaMemcpyAsync(w2.data(), s->sp_work, w2.size() * sizeof(int4), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    sim_free(s, s->sp_trace);
+    s->sp_trace = nullptr;
+    if (rc) return rc;
+    unsigned long long t0 = ~0ull;
+    for (int i = 0; i < s->sp_items; ++i) t0 = std::min(t0, t[4 * (size_t)i]);
+    for (int i = 0; i < s->sp_items; ++i) {
+        for (int k = 0; k < 3; ++k) out[4 * (size_t)i + k] = (int64_t)(t[4 * (size_t)i + k] - t0);
+        out[4 * (size_t)i + 3] = (int64_t)t[4 * (size_t)i + 3];
+        if (planes) { planes[2 * i] = w2[2 * i].z; planes[2 * i + 1] = w2[2 * i].w; }
+    }
     return 0;
 }
 
