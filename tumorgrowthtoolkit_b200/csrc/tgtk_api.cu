@@ -130,6 +130,7 @@ struct tgtk_sim {
     size_t sp_live_cap = 0, sp_work_cap = 0;
     int sp_items = 0, sp_nzt = 0, sp_nyt = 0;
     int64_t sp_live_voxels = 0;      // voxels in live warp tiles
+    bool sp_waves_set = false;
     double sp_waves = 1.0;           // work items per resident-block slot (TGTK_SP_WAVES); measured best: one (every item pays a 3 us prologue)
     int sp_carveout = -1;
     int64_t sp_min_voxels = 1 << 18;  // TGTK_SPARSE_MIN_VOXELS
@@ -1047,31 +1048,40 @@ static int build_sparse_inner(tgtk_sim *s)
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
     s->sp_per_sm = per_sm;
     if (s->sp_ahead < 0) s->sp_ahead = sms * per_sm;
-    // a slot's share of the work, cut into `waves` items; two items per slot: the first one takes `split` of it, so that
-    // the blocks of the second round are the short ones and the launch ends evenly
-    const double floor_w = 4.0 * (kBase + 4.0);       // at least ~4 full planes per item: every item pays a prologue
-    const double share = total / ((double)sms * per_sm);
-    const bool two = std::fabs(s->sp_waves - 2.0) < 1e-9;
-    const double tgt[2] = {std::max(two ? share * s->sp_split : share / s->sp_waves, floor_w),
-                           std::max(two ? share * (1.0 - s->sp_split) : share / s->sp_waves, floor_w)};
+    // A slot's share of the work, cut into `waves` items (two per slot: the first takes `split` of it).  One item per slot is
+    // best while a slot's share is short -- every item pays a 3 us prologue (tools/sparse_trace.py) -- and then the list must
+    // FIT the resident slots: a handful of items too many would run as a second round of their own and double the launch.
+    // Long shares (big boxes) are cut into rounds of ~20 planes, which the hardware's block scheduler balances by itself.
+    const double floor_w = 4.0 * (kBase + 4.0 * kWarp);       // at least ~4 full planes per item
+    const double slots = (double)sms * per_sm;
+    const double share = total / slots;
+    double waves = s->sp_waves;
+    if (!s->sp_waves_set) waves = std::max(1.0, std::floor(share / (20.0 * (kBase + 4.0 * kWarp))));
+    const bool two = std::fabs(waves - 2.0) < 1e-9;
     std::vector<Run> items;
-    int turn = 0;
-    for (const Run &r : runs) {
-        int x0 = r.x0;
-        double acc = 0.0, left = r.w;
-        for (int q = r.x0; q < r.x1; ++q) {
-            const double c = cost(at(q, r.zt, r.yt));
-            acc += c;
-            left -= c;
-            const bool last = (q + 1 == r.x1);
-            // cut when the item has reached its size and what is left of the run is worth an item of its own
-            if (last || (acc >= tgt[turn] - 1e-9 && left >= 0.5 * std::min(tgt[0], tgt[1]))) {
-                items.push_back({r.yt, r.zt, x0, q + 1, acc});
-                x0 = q + 1;
-                acc = 0.0;
-                turn ^= 1;
+    for (double grow = 1.0; grow < 3.0; grow *= 1.04) {
+        const double tgt[2] = {std::max((two ? share * s->sp_split : share / waves) * grow, floor_w),
+                               std::max((two ? share * (1.0 - s->sp_split) : share / waves) * grow, floor_w)};
+        items.clear();
+        int turn = 0;
+        for (const Run &r : runs) {
+            int x0 = r.x0;
+            double acc = 0.0, left = r.w;
+            for (int q = r.x0; q < r.x1; ++q) {
+                const double c = cost(at(q, r.zt, r.yt));
+                acc += c;
+                left -= c;
+                const bool last = (q + 1 == r.x1);
+                // cut when the item has reached its size and what is left of the run is worth an item of its own
+                if (last || (acc >= tgt[turn] - 1e-9 && left >= 0.5 * std::min(tgt[0], tgt[1]))) {
+                    items.push_back({r.yt, r.zt, x0, q + 1, acc});
+                    x0 = q + 1;
+                    acc = 0.0;
+                    turn ^= 1;
+                }
             }
         }
+        if (waves >= 3.0 || (double)items.size() <= slots * std::ceil(waves - 1e-9)) break;
     }
     std::stable_sort(items.begin(), items.end(), [](const Run &a, const Run &b) { return a.w > b.w; });   // longest first
     std::vector<int4> work(2 * items.size());
@@ -1502,7 +1512,7 @@ int tgtk_sim_create_ex(tgtk_sim **out, const tgtk_params *params, int device, vo
     if (const char *v = getenv("TGTK_ZIGZAG")) s->zigzag = atoi(v) != 0;
     if (const char *v = getenv("TGTK_CLOSED_SKIP")) s->closed_skip = atoi(v) != 0;
     if (const char *v = getenv("TGTK_SPARSE")) s->sparse = atoi(v);
-    if (const char *v = getenv("TGTK_SP_WAVES")) s->sp_waves = std::max(0.25, atof(v));
+    if (const char *v = getenv("TGTK_SP_WAVES")) { s->sp_waves = std::max(0.25, atof(v)); s->sp_waves_set = true; }
     if (const char *v = getenv("TGTK_SP_ASYNC")) s->sp_async = atoi(v);
     if (const char *v = getenv("TGTK_SPARSE_MIN_VOXELS")) s->sp_min_voxels = atoll(v);
     if (const char *v = getenv("TGTK_SP_AHEAD")) s->sp_ahead = atoi(v);
