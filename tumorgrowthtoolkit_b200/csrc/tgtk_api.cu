@@ -585,24 +585,18 @@ template <typename T> static cudaError_t launch_step(tgtk_sim *s)
         }
     }
     if (s->sy != s->p.Z) s->pads_dirty = true;   // no other kernel maintains the z = 0 mirror
-    // the fused slab driver (and the serpentine sweep) run dedicated instantiations of the two-voxel kernels, 32 x 4 threads
-    if (s->lx > 0 && effective_variant(s) == 4 && slab_kernels(s)) {
-        switch (s->p.model) {
-        case TGTK_MODEL_FK: return launch_v4(s, fk_step_v4<T, 32, 4, 8, 1>, a, s->lx);
-        case TGTK_MODEL_DTI: return launch_v4(s, dti_step_v4<T, 32, 4, 8, 1>, a, s->lx);
-        case TGTK_MODEL_FK_2C:
-            if (sizeof(T) == 8) return launch_v4(s, fk2c_step_v4<T, 32, 4, 4, 0, 1>, a, s->lx);
-            return launch_v4(s, fk2c_step_v4<T, 32, 4, 6, 0, 1>, a, s->lx);
-        default: break;
-        }
-    }
     if (s->sp_active && s->lx > 0 && effective_variant(s) == 4) {   // work list over the live tiles
         const dim3 g = s->grid, b = s->block;
         s->grid = dim3((unsigned)s->sp_items, 1, 1);
         s->block = dim3(32, 4, 1);
         const SparseArgs sp = {s->sp_live, s->sp_work, s->sp_ahead, s->sp_nzt, s->sp_nyt, s->sp_trace};
         cudaError_t e;
-        if (s->p.model == TGTK_MODEL_FK) e = launch_v4(s, fk_step_sp<T, 8>, a, sp);
+        if (s->slab_on) {           // fused slab driver: the instantiations with the halo push and the flag protocol
+            if (s->p.model == TGTK_MODEL_FK) e = launch_v4(s, fk_step_sp<T, 8, 1>, a, sp);
+            else if (s->p.model == TGTK_MODEL_DTI) e = launch_v4(s, dti_step_sp<T, 8, 1>, a, sp);
+            else if constexpr (sizeof(T) == 8) e = launch_v4(s, fk2c_step_sp<T, 4, 1>, a, sp);
+            else e = launch_v4(s, fk2c_step_sp<T, 6, 1>, a, sp);
+        } else if (s->p.model == TGTK_MODEL_FK) e = launch_v4(s, fk_step_sp<T, 8>, a, sp);
         else if (s->p.model == TGTK_MODEL_DTI) e = launch_v4(s, dti_step_sp<T, 8>, a, sp);
         else if constexpr (sizeof(T) == 8) {
             if (s->sp_async == 2 && s->sp_minb == 5) e = launch_v4(s, fk2c_step_spa<T, 5, 2>, a, sp);
@@ -615,6 +609,17 @@ template <typename T> static cudaError_t launch_step(tgtk_sim *s)
         s->grid = g;
         s->block = b;
         return e;
+    }
+    // the fused slab driver (and the serpentine sweep) run dedicated instantiations of the two-voxel kernels, 32 x 4 threads
+    if (s->lx > 0 && effective_variant(s) == 4 && slab_kernels(s)) {
+        switch (s->p.model) {
+        case TGTK_MODEL_FK: return launch_v4(s, fk_step_v4<T, 32, 4, 8, 1>, a, s->lx);
+        case TGTK_MODEL_DTI: return launch_v4(s, dti_step_v4<T, 32, 4, 8, 1>, a, s->lx);
+        case TGTK_MODEL_FK_2C:
+            if (sizeof(T) == 8) return launch_v4(s, fk2c_step_v4<T, 32, 4, 4, 0, 1>, a, s->lx);
+            return launch_v4(s, fk2c_step_v4<T, 32, 4, 6, 0, 1>, a, s->lx);
+        default: break;
+        }
     }
     if (s->lx > 0 && effective_variant(s) == 4 && s->p.model == TGTK_MODEL_FK) {
         if (s->block.x == 16) return launch_v4(s, fk_step_v4<T, 16, 8, 8>, a, s->lx);
@@ -945,7 +950,7 @@ static bool tb_enabled(const tgtk_sim *s);
 static bool sparse_eligible(const tgtk_sim *s)
 {
     const tgtk_params &p = s->p;
-    if (s->sparse == 0 || s->sp_forbid || s->slab_on) return false;
+    if (s->sparse == 0 || (s->sp_forbid && !s->slab_on)) return false;      // (the fused slab driver only READS through its buffer views)
     if (p.model != TGTK_MODEL_FK_2C && p.model != TGTK_MODEL_FK && p.model != TGTK_MODEL_DTI) return false;
     const bool dti32_auto = s->variant == 0 && p.dtype == TGTK_F32 && p.model == TGTK_MODEL_DTI;      // runs the z-pair kernels unless sparse
     if (s->lx <= 0 || (!dti32_auto && effective_variant(s) != 4) || p.X < 8) return false;
@@ -992,10 +997,12 @@ static int build_sparse_inner(tgtk_sim *s)
     CU(cudaMemcpyAsync(live.data(), s->sp_live, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
 
-    // voxels in live warp tiles (the bytes a sparse launch has to move are proportional to it)
+    // voxels in live warp tiles (the bytes a sparse launch has to move are proportional to it); fused slab mode: of the
+    // planes this rank owns -- the ghost planes are the neighbours' to compute
+    const int xa = s->slab_on ? 1 : 0, xb = s->slab_on ? 1 + s->slab_owned : p.X;
     int64_t live_vox = 0;
     auto at = [&](int x, int zt, int yt) { return live[((size_t)x * nzt + zt) * nyt + yt]; };
-    for (int x = 0; x < p.X; ++x)
+    for (int x = xa; x < xb; ++x)
         for (int zt = 0; zt < nzt; ++zt)
             for (int yt = 0; yt < nyt; ++yt) {
                 const uint32_t w = at(x, zt, yt);
@@ -1004,7 +1011,8 @@ static int build_sparse_inner(tgtk_sim *s)
                     if ((w >> (8 * k)) & 0xffu) live_vox += (int64_t)zs * std::max(0, std::min(2, p.Y - (yt * 8 + 2 * k)));
             }
     s->sp_live_voxels = live_vox;
-    if (s->sparse < 0 && (double)live_vox > 0.9 * (double)s->n) { if (was) drop_graph(s); return 0; }   // nothing to gain
+    const double owned_vox = (double)(xb - xa) * p.Y * p.Z;
+    if (s->sparse < 0 && (double)live_vox > 0.9 * owned_vox) { if (was) drop_graph(s); return 0; }   // nothing to gain
     if (live_vox == 0) { if (was) drop_graph(s); return 0; }                                             // (and nothing to launch)
 
     // runs of planes with live tiles per (y tile, z tile) column; a gap of kGap dead planes ends a run
@@ -1020,13 +1028,13 @@ static int build_sparse_inner(tgtk_sim *s)
     double total = 0.0;
     for (int zt = 0; zt < nzt; ++zt)
         for (int yt = 0; yt < nyt; ++yt) {
-            int x = 0;
-            while (x < p.X) {
-                while (x < p.X && !at(x, zt, yt)) ++x;
-                if (x >= p.X) break;
+            int x = xa;
+            while (x < xb) {
+                while (x < xb && !at(x, zt, yt)) ++x;
+                if (x >= xb) break;
                 int x0 = x, last = x;
                 double w = 0.0;
-                for (; x < p.X && x - last <= kGap; ++x)
+                for (; x < xb && x - last <= kGap; ++x)
                     if (at(x, zt, yt)) last = x;
                 for (int q = x0; q <= last; ++q) w += cost(at(q, zt, yt));
                 runs.push_back({yt, zt, x0, last + 1, w});
@@ -1084,6 +1092,8 @@ static int build_sparse_inner(tgtk_sim *s)
         if (waves >= 3.0 || (double)items.size() <= slots * std::ceil(waves - 1e-9)) break;
     }
     std::stable_sort(items.begin(), items.end(), [](const Run &a, const Run &b) { return a.w > b.w; });   // longest first
+    if (s->slab_on)     // ... and the items that wait for a neighbour's word last: by then it has long arrived (block 0 publishes)
+        std::stable_partition(items.begin(), items.end(), [&](const Run &r) { return r.x0 != xa && r.x1 != xb; });
     std::vector<int4> work(2 * items.size());
     auto word = [&](const Run &r, int d) { return (int)at((r.x0 + d) % p.X, r.zt, r.yt); };
     for (size_t i = 0; i < items.size(); ++i) {
@@ -1621,7 +1631,7 @@ int tgtk_sim_sparse_info(tgtk_sim *s, int64_t out[4])
     if (!s || !out) return fail("tgtk_sim_sparse_info", "null argument");
     if (!s->prepared) return fail("tgtk_sim_sparse_info", "call tgtk_sim_prepare first");
     CU(cudaSetDevice(s->device));
-    if ((s->sp_dirty || s->sp_active != sparse_eligible(s)) && (s->sp_active || sparse_eligible(s)) && build_sparse(s)) return 1;
+    if (!s->slab_on && (s->sp_dirty || s->sp_active != sparse_eligible(s)) && (s->sp_active || sparse_eligible(s)) && build_sparse(s)) return 1;
     out[0] = s->sp_active ? s->sp_items : 0;
     out[1] = s->sp_active ? s->sp_live_voxels : (int64_t)s->n;
     out[2] = (int64_t)s->n;
@@ -1889,7 +1899,9 @@ int tgtk_sim_run(tgtk_sim *s, int nsteps, const int32_t *record_steps, int nreco
     if (nsteps < 0) return fail("tgtk_sim_run", "negative step count");
     CU(cudaSetDevice(s->device));
     if (s->pads_dirty && zpair_variant(s) && refresh_pads(s)) return 1;
-    if ((s->sp_dirty || s->sp_active != sparse_eligible(s)) && (s->sp_active || sparse_eligible(s)) && build_sparse(s)) return 1;
+    if (s->slab_on) {
+        if (s->sp_dirty && s->sp_active) { s->sp_active = false; drop_graph(s); }      // see tgtk_sim_slab_attach
+    } else if ((s->sp_dirty || s->sp_active != sparse_eligible(s)) && (s->sp_active || sparse_eligible(s)) && build_sparse(s)) return 1;
     if (ensure_volumes(s, s->t_enqueued + nsteps)) return 1;
     s->ctrl_valid = false;
     const size_t bytes = (size_t)s->p.X * s->sx * s->elem;

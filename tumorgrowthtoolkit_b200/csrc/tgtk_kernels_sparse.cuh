@@ -214,7 +214,7 @@ __device__ __forceinline__ void sparse_prefetch_item(const StepArgs<T> &a, const
 }
 
 // ---- FK_2c ---------------------------------------------------------------------------------------------------------
-template <typename T, int MINB>
+template <typename T, int MINB, int SLAB = 0>
 __global__ void __launch_bounds__(128, MINB) fk2c_step_sp(const StepArgs<T> a, const SparseArgs sp)
 {
     constexpr int TZ = 32, TYV = 8, RS = TZ + 2, PL = (TYV + 2) * RS;
@@ -246,6 +246,13 @@ __global__ void __launch_bounds__(128, MINB) fk2c_step_sp(const StepArgs<T> a, c
     double sP = 0.0, sN = 0.0;
     griddep_launch();
     griddep_wait();
+    // fused slab mode (tgtk_common.cuh: slab_begin): item 0 publishes the epoch, an item that starts on the rank's lowest /
+    // ends on its highest owned plane waits for that neighbour's word, reads its ghost plane and pushes its boundary plane
+    const SlabCtl sl = SLAB ? slab_begin(a, g.x0, g.x1) : SlabCtl{false, false, 0};
+    auto push = [&](T *const *peer, uint32_t off, T pn0, T nn0, T sn0, T pn1, T nn1, T sn1) {
+        if (g.valid0) { peer[0][g.c0 + off] = pn0; peer[1][g.c0 + off] = nn0; peer[2][g.c0 + off] = sn0; }
+        if (g.valid1) { peer[0][g.c1 + off] = pn1; peer[1][g.c1 + off] = nn1; peer[2][g.c1 + off] = sn1; }
+    };
 
     Vox2c<T> A0, A1, B0, B1;               // rows (y, y+1) of plane x (A) and plane x+1 (B); roles swap
     bool liveA = (lw.w0 >> sh) & 0xffu, liveB = false;
@@ -348,6 +355,8 @@ __global__ void __launch_bounds__(128, MINB) fk2c_step_sp(const StepArgs<T> a, c
                 Po[g.c1] = pn1; No[g.c1] = nn1; So[g.c1] = sn1;
                 if (cnt) { sP += (double)pn1; sN += (double)nn1; }
             }
+            if (SLAB && sl.lo && x == a.x_lo) { push(a.peer_lo[sc.par ^ 1], a.off_lo, pn0, nn0, sn0, pn1, nn1, sn1); }
+            if (SLAB && sl.hi && x == a.x_hi - 1) { push(a.peer_hi[sc.par ^ 1], a.off_hi, pn0, nn0, sn0, pn1, nn1, sn1); }
 #ifdef TGTK_SP_PHASES
             SP_CLOCK(k6, sP);
             ph[0] += k1 - k0; ph[1] += k2 - k1; ph[2] += k3 - k2; ph[3] += k4 - k3; ph[4] += k5 - k4; ph[5] += k6 - k5;
@@ -585,7 +594,7 @@ __global__ void __launch_bounds__(128, MINB) fk2c_step_spa(const StepArgs<T> a, 
 }
 
 // ---- FK ----------------------------------------------------------------------------------------------------------------
-template <typename T, int MINB>
+template <typename T, int MINB, int SLAB = 0>
 __global__ void __launch_bounds__(128, MINB) fk_step_sp(const StepArgs<T> a, const SparseArgs sp)
 {
     constexpr int TZ = 32, TYV = 8, RS = TZ + 2, PL = (TYV + 2) * RS;
@@ -610,6 +619,11 @@ __global__ void __launch_bounds__(128, MINB) fk_step_sp(const StepArgs<T> a, con
     double s = 0.0;
     griddep_launch();
     griddep_wait();
+    const SlabCtl sl = SLAB ? slab_begin(a, g.x0, g.x1) : SlabCtl{false, false, 0};
+    auto push = [&](T *const *peer, uint32_t off, T v0, T v1) {
+        if (g.valid0) peer[0][g.c0 + off] = v0;
+        if (g.valid1) peer[0][g.c1 + off] = v1;
+    };
 
     VoxFk<T> A0, A1, B0, B1;
     bool liveA = (lw.w0 >> sh) & 0xffu, liveB = false;
@@ -658,6 +672,8 @@ __global__ void __launch_bounds__(128, MINB) fk_step_sp(const StepArgs<T> a, con
             const bool cnt = counts(a, x);
             if (g.valid0) { out[g.c0] = un0; if (cnt) s += (double)un0; }
             if (g.valid1) { out[g.c1] = un1; if (cnt) s += (double)un1; }
+            if (SLAB && sl.lo && x == a.x_lo) { push(a.peer_lo[sc.par ^ 1], a.off_lo, un0, un1); }
+            if (SLAB && sl.hi && x == a.x_hi - 1) { push(a.peer_hi[sc.par ^ 1], a.off_hi, un0, un1); }
         }
         g.c0 = n0; g.c1 = n1;
         buf ^= 1;
@@ -675,7 +691,7 @@ __global__ void __launch_bounds__(128, MINB) fk_step_sp(const StepArgs<T> a, con
 }
 
 // ---- FK_DTI (reference rounding order, bitwise equal to dti_step_v4) -----------------------------------------------------
-template <typename T, int MINB>
+template <typename T, int MINB, int SLAB = 0>
 __global__ void __launch_bounds__(128, MINB) dti_step_sp(const StepArgs<T> a, const SparseArgs sp)
 {
     using R = Rn<T>;
@@ -702,6 +718,11 @@ __global__ void __launch_bounds__(128, MINB) dti_step_sp(const StepArgs<T> a, co
     auto none = [&](VoxDti<T> &v) { v.u = T(0); v.d0 = T(0); v.d1 = T(0); v.d2 = T(0); };
     griddep_launch();
     griddep_wait();
+    const SlabCtl sl = SLAB ? slab_begin(a, g.x0, g.x1) : SlabCtl{false, false, 0};
+    auto push = [&](T *const *peer, uint32_t off, T v0, T v1) {
+        if (g.valid0) peer[0][g.c0 + off] = v0;
+        if (g.valid1) peer[0][g.c1 + off] = v1;
+    };
 
     VoxDti<T> A0, A1, B0, B1;
     bool liveA = (lw.w0 >> sh) & 0xffu, liveB = false;
@@ -742,6 +763,8 @@ __global__ void __launch_bounds__(128, MINB) dti_step_sp(const StepArgs<T> a, co
             const bool cnt = counts(a, x);
             if (g.valid0) { out[g.c0] = un0; if (cnt) s += (double)un0; }
             if (g.valid1) { out[g.c1] = un1; if (cnt) s += (double)un1; }
+            if (SLAB && sl.lo && x == a.x_lo) { push(a.peer_lo[sc.par ^ 1], a.off_lo, un0, un1); }
+            if (SLAB && sl.hi && x == a.x_hi - 1) { push(a.peer_hi[sc.par ^ 1], a.off_hi, un0, un1); }
         }
         um0 = c0.u; um1 = c1.u;
         g.c0 = n0; g.c1 = n1;
