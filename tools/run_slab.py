@@ -58,7 +58,9 @@ def main():
                                                   precision=args.precision, device=local, **kw)
     if args.stop_fraction > 0:
         probe = call(slab, max(1, int(args.stop_fraction * args.steps)), halo=halo, driver=args.driver)
-        extra["stopping_volume"] = probe["volume"]
+        # just below the volume the probe reached: the decomposed and the undecomposed run sum their partial volumes in
+        # different orders (last-bit differences), a threshold EXACTLY on a reached volume would let them stop one step apart
+        extra["stopping_volume"] = probe["volume"] * (1.0 - 1e-9)
 
     def timed():
         torch.cuda.synchronize()
