@@ -702,6 +702,7 @@ def main():
                 one_step()
     st = sim.sync()
     final_volume = st.last_volume
+    tuning = sim.tuning()               # (after the loop: FK_DTI fp32 picks its kernel family with the sparse mask, at the first run)
     sparse = sim.sparse_info()          # sparse launches: tiles outside the tissue are never loaded / stored (include/tgtk_b200.h)
     # the same loop with the exact per-warp shortcuts for tumour-free / background warps switched off (reported beside the headline)
     dense = None

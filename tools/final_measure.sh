@@ -24,6 +24,13 @@ for f in sorted(glob.glob("$O/bench_*.json")):
 PY
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_fk2c_fp64.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $O/ncu_list.log 2>&1
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:fk2c_step --launch-skip 300 --launch-count 1 -o $O/fk2c_fp64_final -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $O/ncu_full.log 2>&1
+python tools/ncu_summary.py $O/fk2c_fp64_final.ncu-rep > $O/fk2c_fp64_final.ncu_summary.txt 2>/dev/null; head -12 $O/fk2c_fp64_final.ncu_summary.txt
+python tools/ncu_by_line.py $O/fk2c_fp64_final.ncu-rep _ZN4tgtk12fk2c_step_spIdLi4ELi0EEEvNS_8StepArgsIT_EENS_10SparseArgsE 25 > $O/fk2c_fp64_final.by_line.txt 2>&1
+# sparse against dense launches on the benchmark box, all six model / precision pairs
+for m in fk2c fk dti; do for p in fp64 fp32; do
+  timeout 200 python tools/sweep_atlas.py --model $m --precision $p TGTK_SPARSE=0,1 2>&1 | tail -3
+done; done > $O/sparse_vs_dense.txt; cat $O/sparse_vs_dense.txt
+timeout 100 python tools/sparse_trace.py > $O/sparse_trace.txt 2>&1; head -7 $O/sparse_trace.txt
 timeout 200 python tools/sweep_env.py --shape 288,354,277 --steps 100 > $O/steps_big.txt 2>&1; cat $O/steps_big.txt
 timeout 200 python tools/sweep_env.py > $O/steps_atlas.txt 2>&1; cat $O/steps_atlas.txt
 timeout 200 python tools/sweep_env.py --shape 95,117,91 > $O/steps_ensemble.txt 2>&1; cat $O/steps_ensemble.txt
