@@ -15,10 +15,18 @@ ap.add_argument("--precision", default="fp64")
 ap.add_argument("--res", type=float, default=1.0)
 ap.add_argument("--steps", type=int, default=400)
 ap.add_argument("--rounds", type=int, default=3)
+ap.add_argument("--planes", default="", help="a:b -- only these planes of axis 0 (what one rank of a slab run owns), as a periodic box")
 args = ap.parse_args()
 keys = [s.split("=")[0] for s in args.settings]
 vals = [s.split("=")[1].split(",") for s in args.settings]
 pb = bench.build_problem(args.model, args.res)
+if args.planes:
+    a, b = (int(v) for v in args.planes.split(":"))
+    cut = lambda v: None if v is None else np.ascontiguousarray(v[a:b])
+    pb["wm"], pb["gm"] = cut(pb["wm"]), cut(pb["gm"])
+    pb["fields"] = {k: cut(v) for k, v in pb["fields"].items()}
+    pb["shape"] = next(iter(pb["fields"].values())).shape[:3]
+    pb["voxels"] = int(np.prod(pb["shape"]))
 print(f"# {args.model} {args.precision} box {pb['shape']} {pb['voxels']} voxels, {args.steps} steps per loop", flush=True)
 combos = list(itertools.product(*vals)) or [()]
 sims = []
