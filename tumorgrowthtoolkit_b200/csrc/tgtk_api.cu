@@ -1056,21 +1056,25 @@ static int build_sparse_inner(tgtk_sim *s)
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
     s->sp_per_sm = per_sm;
     if (s->sp_ahead < 0) s->sp_ahead = sms * per_sm;
-    // A slot's share of the work, cut into `waves` items (two per slot: the first takes `split` of it).  One item per slot is
-    // best while a slot's share is short -- every item pays a 3 us prologue (tools/sparse_trace.py) -- and then the list must
-    // FIT the resident slots: a handful of items too many would run as a second round of their own and double the launch.
-    // Long shares (big boxes) are cut into rounds of ~20 planes, which the hardware's block scheduler balances by itself.
-    const double floor_w = 4.0 * (kBase + 4.0 * kWarp);       // at least ~4 full planes per item
-    const double slots = (double)sms * per_sm;
+    // The list: every column's runs cut into items of a target size.  Which size is decided by trying a few -- a slot's
+    // share of the work in 1, 1.5, 2, 3, 4, 6 or 8 items -- and playing each list through the hardware's block scheduler
+    // (blocks start in list order on the slot that frees first; an item costs its planes plus a prologue worth ~1.75 planes,
+    // tools/sparse_trace.py): one item per slot avoids prologues but ends unevenly and falls off a cliff when the list is
+    // a handful of items longer than the resident slots; many short items balance by themselves but pay for it.
+    const double plane = kBase + 2.5 * kWarp, prologue = 1.75 * plane;
+    const double floor_w = 4.0 * plane;                        // at least ~4 full planes per item
+    const int slots = sms * per_sm;
     const double share = total / slots;
-    double waves = s->sp_waves;
-    if (!s->sp_waves_set) waves = std::max(1.0, std::floor(share / (20.0 * (kBase + 4.0 * kWarp))));
-    const bool two = std::fabs(waves - 2.0) < 1e-9;
-    std::vector<Run> items;
-    for (double grow = 1.0; grow < 3.0; grow *= 1.04) {
-        const double tgt[2] = {std::max((two ? share * s->sp_split : share / waves) * grow, floor_w),
-                               std::max((two ? share * (1.0 - s->sp_split) : share / waves) * grow, floor_w)};
-        items.clear();
+    auto order = [&](std::vector<Run> &v) {
+        std::stable_sort(v.begin(), v.end(), [](const Run &a, const Run &b) { return a.w > b.w; });   // longest first
+        if (s->slab_on)     // ... and the items that wait for a neighbour's word last: by then it has long arrived
+            std::stable_partition(v.begin(), v.end(), [&](const Run &r) { return r.x0 != xa && r.x1 != xb; });
+    };
+    auto cut = [&](double waves, std::vector<Run> &out) {
+        const bool two = std::fabs(waves - 2.0) < 1e-9;
+        const double tgt[2] = {std::max(two ? share * s->sp_split : share / waves, floor_w),
+                               std::max(two ? share * (1.0 - s->sp_split) : share / waves, floor_w)};
+        out.clear();
         int turn = 0;
         for (const Run &r : runs) {
             int x0 = r.x0;
@@ -1082,18 +1086,39 @@ static int build_sparse_inner(tgtk_sim *s)
                 const bool last = (q + 1 == r.x1);
                 // cut when the item has reached its size and what is left of the run is worth an item of its own
                 if (last || (acc >= tgt[turn] - 1e-9 && left >= 0.5 * std::min(tgt[0], tgt[1]))) {
-                    items.push_back({r.yt, r.zt, x0, q + 1, acc});
+                    out.push_back({r.yt, r.zt, x0, q + 1, acc});
                     x0 = q + 1;
                     acc = 0.0;
                     turn ^= 1;
                 }
             }
         }
-        if (waves >= 3.0 || (double)items.size() <= slots * std::ceil(waves - 1e-9)) break;
+        order(out);
+    };
+    auto makespan = [&](const std::vector<Run> &v) {
+        std::vector<double> heap((size_t)slots, 0.0);          // min-heap of the slots' free times
+        auto cmp = [](double a, double b) { return a > b; };
+        double end = 0.0;
+        for (const Run &r : v) {
+            std::pop_heap(heap.begin(), heap.end(), cmp);
+            heap.back() += r.w + prologue;
+            end = std::max(end, heap.back());
+            std::push_heap(heap.begin(), heap.end(), cmp);
+        }
+        return end;
+    };
+    std::vector<Run> items, trial;
+    if (s->sp_waves_set) {
+        cut(s->sp_waves, items);
+    } else {
+        double best = 1e300;
+        for (double w : {1.0, 1.5, 2.0, 3.0, 4.0, 6.0, 8.0}) {
+            if (w > 1.0 && share / w < floor_w) break;
+            cut(w, trial);
+            const double t = makespan(trial);
+            if (t < best * 0.98) { best = t; items.swap(trial); }      // (a finer list has to win by 2 %)
+        }
     }
-    std::stable_sort(items.begin(), items.end(), [](const Run &a, const Run &b) { return a.w > b.w; });   // longest first
-    if (s->slab_on)     // ... and the items that wait for a neighbour's word last: by then it has long arrived (block 0 publishes)
-        std::stable_partition(items.begin(), items.end(), [&](const Run &r) { return r.x0 != xa && r.x1 != xb; });
     std::vector<int4> work(2 * items.size());
     auto word = [&](const Run &r, int d) { return (int)at((r.x0 + d) % p.X, r.zt, r.yt); };
     for (size_t i = 0; i < items.size(); ++i) {
