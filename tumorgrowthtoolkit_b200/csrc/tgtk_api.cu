@@ -1056,8 +1056,8 @@ static int build_sparse_inner(tgtk_sim *s)
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
     s->sp_per_sm = per_sm;
     if (s->sp_ahead < 0) s->sp_ahead = sms * per_sm;
-    // The list: every column's runs cut into items of a target size.  Which size is decided by trying a few -- a slot's
-    // share of the work in 1, 1.5, 2, 3, 4, 6 or 8 items -- and playing each list through the hardware's block scheduler
+    // The list: every column's runs cut into items of a target size.  For long shares (big boxes) the size is decided by
+    // trying a few -- a slot's share of the work in 1, 1.5, 2, 3, 4, 6 or 8 items -- and playing each list through the block scheduler
     // (blocks start in list order on the slot that frees first; an item costs its planes plus a prologue worth ~1.75 planes,
     // tools/sparse_trace.py): one item per slot avoids prologues but ends unevenly and falls off a cliff when the list is
     // a handful of items longer than the resident slots; many short items balance by themselves but pay for it.
@@ -1070,10 +1070,10 @@ static int build_sparse_inner(tgtk_sim *s)
         if (s->slab_on)     // ... and the items that wait for a neighbour's word last: by then it has long arrived
             std::stable_partition(v.begin(), v.end(), [&](const Run &r) { return r.x0 != xa && r.x1 != xb; });
     };
-    auto cut = [&](double waves, std::vector<Run> &out) {
+    auto cut = [&](double waves, std::vector<Run> &out, double grow = 1.0) {
         const bool two = std::fabs(waves - 2.0) < 1e-9;
-        const double tgt[2] = {std::max(two ? share * s->sp_split : share / waves, floor_w),
-                               std::max(two ? share * (1.0 - s->sp_split) : share / waves, floor_w)};
+        const double tgt[2] = {std::max((two ? share * s->sp_split : share / waves) * grow, floor_w),
+                               std::max((two ? share * (1.0 - s->sp_split) : share / waves) * grow, floor_w)};
         out.clear();
         int turn = 0;
         for (const Run &r : runs) {
@@ -1110,13 +1110,20 @@ static int build_sparse_inner(tgtk_sim *s)
     std::vector<Run> items, trial;
     if (s->sp_waves_set) {
         cut(s->sp_waves, items);
+    } else if (share < 20.0 * plane) {
+        // short shares: ONE item per slot, sized up until the list fits the resident slots.  (Measured on the atlas box: the
+        // model below would pick two rounds for FK_2c and lose 2 % -- it does not know that the blocks left on an SM speed
+        // up when their neighbours have finished, which evens out a single round by itself.)
+        for (double grow = 1.0; grow < 3.0; grow *= 1.04) {
+            cut(1.0, items, grow);
+            if ((int)items.size() <= slots) break;
+        }
     } else {
         double best = 1e300;
         for (double w : {1.0, 1.5, 2.0, 3.0, 4.0, 6.0, 8.0}) {
-            if (w > 1.0 && share / w < floor_w) break;
             cut(w, trial);
             const double t = makespan(trial);
-            if (t < best * 0.98) { best = t; items.swap(trial); }      // (a finer list has to win by 2 %)
+            if (t < best * 0.95) { best = t; items.swap(trial); }      // (a finer list has to win by 5 %)
         }
     }
     std::vector<int4> work(2 * items.size());
