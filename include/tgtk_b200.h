@@ -141,6 +141,13 @@ int tgtk_sim_sparse_info(tgtk_sim *sim, int64_t out[4]);
  * first block's start to this block's start / to the end of its prologue / to the end of its plane loop, out[4*i + 3] = the SM
  * it ran on; planes[2*i + 0..1] = its plane range (may be NULL).  cap: items the arrays hold (>= tgtk_sim_sparse_info out[0]). */
 int tgtk_sim_sparse_trace(tgtk_sim *sim, int64_t *out, int32_t *planes, int cap);
+/* The work-list planner of the sparse launches as a pure host function (no device needed; tests/test_sparse_plan.py).
+ * mask[(x * nzt + zt) * nyt + yt]: one word per 8 x 32 block tile of plane x, byte w = the tile's rows 2w, 2w+1 hold a live
+ * voxel.  Planes [x_lo, x_hi) are to be computed (a slab rank: its owned planes), `slots` = resident blocks of the device
+ * for the kernel, slab != 0: items that start on x_lo or end on x_hi go last.  items[4*i + 0..3] = y tile, z tile, first
+ * plane, end plane of item i (launch order); *count = number of items (items may be NULL to query it). */
+int tgtk_sparse_plan_host(const uint32_t *mask, int X, int nzt, int nyt, int x_lo, int x_hi, int slots, int slab, int32_t *items,
+                          int cap, int *count);
 
 /* Slab decomposition support.  set_sum_range: only planes [x0, x1) of axis 0 count towards the
  * volume (a rank's owned planes; its ghost planes are stepped but not summed).  buffer_ptr: device

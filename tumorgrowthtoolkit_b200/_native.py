@@ -111,6 +111,8 @@ def lib():
     L.tgtk_sim_get_tuning.argtypes = [vp, ctypes.POINTER(ctypes.c_int32 * 10)]
     L.tgtk_sim_sparse_info.argtypes = [vp, ctypes.POINTER(ctypes.c_int64 * 4)]
     L.tgtk_sim_sparse_trace.argtypes = [vp, ctypes.POINTER(ctypes.c_int64), ip, ctypes.c_int]
+    L.tgtk_sparse_plan_host.argtypes = [ctypes.POINTER(ctypes.c_uint32), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_int, ip, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
     L.tgtk_sim_reset.argtypes = [vp]
     L.tgtk_sim_run.argtypes = [vp, ctypes.c_int, ip, ctypes.c_int]
     L.tgtk_sim_sync.argtypes = [vp, ctypes.POINTER(Status)]
@@ -156,6 +158,21 @@ def _as_f64(a):
 
 def _strides(a):
     return _I64x3(*[s // a.itemsize for s in a.strides])
+
+
+def sparse_plan(mask, x_lo=0, x_hi=None, slots=592, slab=False):
+    """The work list of a sparse launch for a tile mask of shape (X, nzt, nyt), uint32 (include/tgtk_b200.h:
+    tgtk_sparse_plan_host; host code only).  Returns an (items, 4) int32 array: y tile, z tile, first plane, end plane."""
+    mask = np.ascontiguousarray(mask, dtype=np.uint32)
+    X, nzt, nyt = mask.shape
+    x_hi = X if x_hi is None else x_hi
+    n = ctypes.c_int(0)
+    mp = mask.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+    _check(lib().tgtk_sparse_plan_host(mp, X, nzt, nyt, int(x_lo), int(x_hi), int(slots), int(bool(slab)), None, 0, ctypes.byref(n)))
+    out = np.zeros((n.value, 4), dtype=np.int32)
+    _check(lib().tgtk_sparse_plan_host(mp, X, nzt, nyt, int(x_lo), int(x_hi), int(slots), int(bool(slab)),
+                                       out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), n.value, ctypes.byref(n)))
+    return out
 
 
 def make_params(model, dtype, shape, h, dt, rho=0.0, Dw=0.0, ratio=1.0, th_matter=0.0, th_necro=0.0,

@@ -944,6 +944,125 @@ static int configure_launch(tgtk_sim *s)
     return 0;
 }
 
+// ---- sparse launches: the work list (pure host code; exported for the CPU tests as tgtk_sparse_plan_host) ------------
+struct PlanOpts {
+    bool slab = false;          // fused slab driver: items that touch plane xa / end on plane xb go last
+    bool waves_set = false;
+    double waves = 1.0, split = 0.5;
+};
+static inline int live_warps(uint32_t w) { return ((w & 0xffu) != 0) + ((w & 0xff00u) != 0) + ((w & 0xff0000u) != 0) + ((w >> 24) != 0); }
+
+// live: [X][nzt][nyt] words; planes [xa, xb) are computed; `slots` = resident blocks of the device for the kernel.
+// Out: two int4 per item -- {y tile, z tile, x0, x1}, {live words of planes x0 .. x0+3 (periodic in X)}.
+static void plan_work_list(const uint32_t *live, int X, int nzt, int nyt, int xa, int xb, int slots, const PlanOpts &o,
+                           std::vector<int4> &work)
+{
+    auto at = [&](int x, int zt, int yt) { return live[((size_t)x * nzt + zt) * nyt + yt]; };
+    // runs of planes with live tiles per (y tile, z tile) column; a gap of kGap dead planes ends a run
+    struct Run { int yt, zt, x0, x1; double w; };
+    const int kGap = 4;
+    // Relative cost of a block plane.  Measured (tools/sparse_trace.py): a plane takes a block 1.5-1.9 us whether one or four
+    // of its warps are live -- the barrier makes the block as slow as its slowest warp -- and a plane without live warps a
+    // fraction of that.  TGTK_SP_COST="base:per_warp:dead".
+    double kBase = 3.4, kWarp = 0.15, kDeadPlane = 0.4;
+    if (const char *v = getenv("TGTK_SP_COST")) sscanf(v, "%lf:%lf:%lf", &kBase, &kWarp, &kDeadPlane);
+    auto cost = [&](uint32_t w) { return w ? kBase + kWarp * live_warps(w) : kDeadPlane; };
+    std::vector<Run> runs;
+    double total = 0.0;
+    for (int zt = 0; zt < nzt; ++zt)
+        for (int yt = 0; yt < nyt; ++yt) {
+            int x = xa;
+            while (x < xb) {
+                while (x < xb && !at(x, zt, yt)) ++x;
+                if (x >= xb) break;
+                int x0 = x, last = x;
+                double w = 0.0;
+                for (; x < xb && x - last <= kGap; ++x)
+                    if (at(x, zt, yt)) last = x;
+                for (int q = x0; q <= last; ++q) w += cost(at(q, zt, yt));
+                runs.push_back({yt, zt, x0, last + 1, w});
+                total += w;
+                x = last + 1;
+            }
+        }
+    // The list: every column's runs cut into items of a target size.  For long shares (big boxes) the size is decided by
+    // trying a few -- a slot's share of the work in 1, 1.5, 2, 3, 4, 6 or 8 items -- and playing each list through the block scheduler
+    // (blocks start in list order on the slot that frees first; an item costs its planes plus a prologue worth ~1.75 planes,
+    // tools/sparse_trace.py): one item per slot avoids prologues but ends unevenly and falls off a cliff when the list is
+    // a handful of items longer than the resident slots; many short items balance by themselves but pay for it.
+    const double plane = kBase + 2.5 * kWarp, prologue = 1.75 * plane;
+    const double floor_w = 4.0 * plane;                        // at least ~4 full planes per item
+    
+    const double share = total / slots;
+    auto order = [&](std::vector<Run> &v) {
+        std::stable_sort(v.begin(), v.end(), [](const Run &a, const Run &b) { return a.w > b.w; });   // longest first
+        if (o.slab)     // ... and the items that wait for a neighbour's word last: by then it has long arrived
+            std::stable_partition(v.begin(), v.end(), [&](const Run &r) { return r.x0 != xa && r.x1 != xb; });
+    };
+    auto cut = [&](double waves, std::vector<Run> &out, double grow = 1.0) {
+        const bool two = std::fabs(waves - 2.0) < 1e-9;
+        const double tgt[2] = {std::max((two ? share * o.split : share / waves) * grow, floor_w),
+                               std::max((two ? share * (1.0 - o.split) : share / waves) * grow, floor_w)};
+        out.clear();
+        int turn = 0;
+        for (const Run &r : runs) {
+            int x0 = r.x0;
+            double acc = 0.0, left = r.w;
+            for (int q = r.x0; q < r.x1; ++q) {
+                const double c = cost(at(q, r.zt, r.yt));
+                acc += c;
+                left -= c;
+                const bool last = (q + 1 == r.x1);
+                // cut when the item has reached its size and what is left of the run is worth an item of its own
+                if (last || (acc >= tgt[turn] - 1e-9 && left >= 0.5 * std::min(tgt[0], tgt[1]))) {
+                    out.push_back({r.yt, r.zt, x0, q + 1, acc});
+                    x0 = q + 1;
+                    acc = 0.0;
+                    turn ^= 1;
+                }
+            }
+        }
+        order(out);
+    };
+    auto makespan = [&](const std::vector<Run> &v) {
+        std::vector<double> heap((size_t)slots, 0.0);          // min-heap of the slots' free times
+        auto cmp = [](double a, double b) { return a > b; };
+        double end = 0.0;
+        for (const Run &r : v) {
+            std::pop_heap(heap.begin(), heap.end(), cmp);
+            heap.back() += r.w + prologue;
+            end = std::max(end, heap.back());
+            std::push_heap(heap.begin(), heap.end(), cmp);
+        }
+        return end;
+    };
+    std::vector<Run> items, trial;
+    if (o.waves_set) {
+        cut(o.waves, items);
+    } else if (share < 20.0 * plane) {
+        // short shares: ONE item per slot, sized up until the list fits the resident slots.  (Measured on the atlas box: the
+        // model below would pick two rounds for FK_2c and lose 2 % -- it does not know that the blocks left on an SM speed
+        // up when their neighbours have finished, which evens out a single round by itself.)
+        for (double grow = 1.0; grow < 3.0; grow *= 1.04) {
+            cut(1.0, items, grow);
+            if ((int)items.size() <= slots) break;
+        }
+    } else {
+        double best = 1e300;
+        for (double w : {1.0, 1.5, 2.0, 3.0, 4.0, 6.0, 8.0}) {
+            cut(w, trial);
+            const double t = makespan(trial);
+            if (t < best * 0.95) { best = t; items.swap(trial); }      // (a finer list has to win by 5 %)
+        }
+    }
+    work.assign(2 * items.size(), make_int4(0, 0, 0, 0));
+    auto word = [&](const Run &r, int d) { return (int)at((r.x0 + d) % X, r.zt, r.yt); };
+    for (size_t i = 0; i < items.size(); ++i) {
+        work[2 * i] = make_int4(items[i].yt, items[i].zt, items[i].x0, items[i].x1);
+        work[2 * i + 1] = make_int4(word(items[i], 0), word(items[i], 1), word(items[i], 2), word(items[i], 3));
+    }
+}
+
 // ---- sparse launches: live-tile mask and work list (tgtk_kernels_sparse.cuh) ---------------------------------------
 static bool tb_enabled(const tgtk_sim *s);
 
@@ -959,7 +1078,6 @@ static bool sparse_eligible(const tgtk_sim *s)
     return !tb_enabled(s);
 }
 
-static inline int live_warps(uint32_t w) { return ((w & 0xffu) != 0) + ((w & 0xff00u) != 0) + ((w & 0xff0000u) != 0) + ((w >> 24) != 0); }
 
 // The mask of the CURRENT state, the copy of that state into the other ping-pong buffer (a dead tile is never written
 // again: both buffers must hold it), the work list.  Synchronises the stream; once per upload.
@@ -1015,33 +1133,6 @@ static int build_sparse_inner(tgtk_sim *s)
     if (s->sparse < 0 && (double)live_vox > 0.9 * owned_vox) { if (was) drop_graph(s); return 0; }   // nothing to gain
     if (live_vox == 0) { if (was) drop_graph(s); return 0; }                                             // (and nothing to launch)
 
-    // runs of planes with live tiles per (y tile, z tile) column; a gap of kGap dead planes ends a run
-    struct Run { int yt, zt, x0, x1; double w; };
-    const int kGap = 4;
-    // Relative cost of a block plane.  Measured (tools/sparse_trace.py): a plane takes a block 1.5-1.9 us whether one or four
-    // of its warps are live -- the barrier makes the block as slow as its slowest warp -- and a plane without live warps a
-    // fraction of that.  TGTK_SP_COST="base:per_warp:dead".
-    double kBase = 3.4, kWarp = 0.15, kDeadPlane = 0.4;
-    if (const char *v = getenv("TGTK_SP_COST")) sscanf(v, "%lf:%lf:%lf", &kBase, &kWarp, &kDeadPlane);
-    auto cost = [&](uint32_t w) { return w ? kBase + kWarp * live_warps(w) : kDeadPlane; };
-    std::vector<Run> runs;
-    double total = 0.0;
-    for (int zt = 0; zt < nzt; ++zt)
-        for (int yt = 0; yt < nyt; ++yt) {
-            int x = xa;
-            while (x < xb) {
-                while (x < xb && !at(x, zt, yt)) ++x;
-                if (x >= xb) break;
-                int x0 = x, last = x;
-                double w = 0.0;
-                for (; x < xb && x - last <= kGap; ++x)
-                    if (at(x, zt, yt)) last = x;
-                for (int q = x0; q <= last; ++q) w += cost(at(q, zt, yt));
-                runs.push_back({yt, zt, x0, last + 1, w});
-                total += w;
-                x = last + 1;
-            }
-        }
     int per_sm = 4, sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
     const bool f64 = (p.dtype == TGTK_F64);
@@ -1056,82 +1147,10 @@ static int build_sparse_inner(tgtk_sim *s)
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
     s->sp_per_sm = per_sm;
     if (s->sp_ahead < 0) s->sp_ahead = sms * per_sm;
-    // The list: every column's runs cut into items of a target size.  For long shares (big boxes) the size is decided by
-    // trying a few -- a slot's share of the work in 1, 1.5, 2, 3, 4, 6 or 8 items -- and playing each list through the block scheduler
-    // (blocks start in list order on the slot that frees first; an item costs its planes plus a prologue worth ~1.75 planes,
-    // tools/sparse_trace.py): one item per slot avoids prologues but ends unevenly and falls off a cliff when the list is
-    // a handful of items longer than the resident slots; many short items balance by themselves but pay for it.
-    const double plane = kBase + 2.5 * kWarp, prologue = 1.75 * plane;
-    const double floor_w = 4.0 * plane;                        // at least ~4 full planes per item
-    const int slots = sms * per_sm;
-    const double share = total / slots;
-    auto order = [&](std::vector<Run> &v) {
-        std::stable_sort(v.begin(), v.end(), [](const Run &a, const Run &b) { return a.w > b.w; });   // longest first
-        if (s->slab_on)     // ... and the items that wait for a neighbour's word last: by then it has long arrived
-            std::stable_partition(v.begin(), v.end(), [&](const Run &r) { return r.x0 != xa && r.x1 != xb; });
-    };
-    auto cut = [&](double waves, std::vector<Run> &out, double grow = 1.0) {
-        const bool two = std::fabs(waves - 2.0) < 1e-9;
-        const double tgt[2] = {std::max((two ? share * s->sp_split : share / waves) * grow, floor_w),
-                               std::max((two ? share * (1.0 - s->sp_split) : share / waves) * grow, floor_w)};
-        out.clear();
-        int turn = 0;
-        for (const Run &r : runs) {
-            int x0 = r.x0;
-            double acc = 0.0, left = r.w;
-            for (int q = r.x0; q < r.x1; ++q) {
-                const double c = cost(at(q, r.zt, r.yt));
-                acc += c;
-                left -= c;
-                const bool last = (q + 1 == r.x1);
-                // cut when the item has reached its size and what is left of the run is worth an item of its own
-                if (last || (acc >= tgt[turn] - 1e-9 && left >= 0.5 * std::min(tgt[0], tgt[1]))) {
-                    out.push_back({r.yt, r.zt, x0, q + 1, acc});
-                    x0 = q + 1;
-                    acc = 0.0;
-                    turn ^= 1;
-                }
-            }
-        }
-        order(out);
-    };
-    auto makespan = [&](const std::vector<Run> &v) {
-        std::vector<double> heap((size_t)slots, 0.0);          // min-heap of the slots' free times
-        auto cmp = [](double a, double b) { return a > b; };
-        double end = 0.0;
-        for (const Run &r : v) {
-            std::pop_heap(heap.begin(), heap.end(), cmp);
-            heap.back() += r.w + prologue;
-            end = std::max(end, heap.back());
-            std::push_heap(heap.begin(), heap.end(), cmp);
-        }
-        return end;
-    };
-    std::vector<Run> items, trial;
-    if (s->sp_waves_set) {
-        cut(s->sp_waves, items);
-    } else if (share < 20.0 * plane) {
-        // short shares: ONE item per slot, sized up until the list fits the resident slots.  (Measured on the atlas box: the
-        // model below would pick two rounds for FK_2c and lose 2 % -- it does not know that the blocks left on an SM speed
-        // up when their neighbours have finished, which evens out a single round by itself.)
-        for (double grow = 1.0; grow < 3.0; grow *= 1.04) {
-            cut(1.0, items, grow);
-            if ((int)items.size() <= slots) break;
-        }
-    } else {
-        double best = 1e300;
-        for (double w : {1.0, 1.5, 2.0, 3.0, 4.0, 6.0, 8.0}) {
-            cut(w, trial);
-            const double t = makespan(trial);
-            if (t < best * 0.95) { best = t; items.swap(trial); }      // (a finer list has to win by 5 %)
-        }
-    }
-    std::vector<int4> work(2 * items.size());
-    auto word = [&](const Run &r, int d) { return (int)at((r.x0 + d) % p.X, r.zt, r.yt); };
-    for (size_t i = 0; i < items.size(); ++i) {
-        work[2 * i] = make_int4(items[i].yt, items[i].zt, items[i].x0, items[i].x1);
-        work[2 * i + 1] = make_int4(word(items[i], 0), word(items[i], 1), word(items[i], 2), word(items[i], 3));
-    }
+    PlanOpts o;
+    o.slab = s->slab_on; o.waves_set = s->sp_waves_set; o.waves = s->sp_waves; o.split = s->sp_split;
+    std::vector<int4> work;
+    plan_work_list(live.data(), p.X, nzt, nyt, xa, xb, sms * per_sm, o, work);
     if (work.size() > s->sp_work_cap) {
         if (s->sp_work) CU(sim_free(s, s->sp_work));
         s->sp_work = nullptr;
@@ -1140,7 +1159,7 @@ static int build_sparse_inner(tgtk_sim *s)
     }
     CU(cudaMemcpyAsync(s->sp_work, work.data(), work.size() * sizeof(int4), cudaMemcpyHostToDevice, s->stream));
     CU(cudaStreamSynchronize(s->stream));
-    s->sp_items = (int)items.size();
+    s->sp_items = (int)(work.size() / 2);
     s->sp_nzt = nzt;
     s->sp_nyt = nyt;
     if ((unsigned)s->sp_items > s->partials_cap) {
@@ -1655,6 +1674,27 @@ int tgtk_sim_get_tuning(tgtk_sim *s, int32_t out[10])
     out[7] = (int32_t)(s->block.x * s->block.y * s->block.z);
     out[8] = tb_enabled(s) ? 2 : 1;
     out[9] = s->sp_active ? s->sp_items : 0;       // work items of a sparse launch (0: dense grid)
+    return 0;
+}
+
+int tgtk_sparse_plan_host(const uint32_t *mask, int X, int nzt, int nyt, int x_lo, int x_hi, int slots, int slab, int32_t *items,
+                          int cap, int *count)
+{
+    if (!mask || !count || X < 1 || nzt < 1 || nyt < 1 || x_lo < 0 || x_hi > X || x_lo >= x_hi || slots < 1)
+        return fail("tgtk_sparse_plan_host", "bad argument");
+    PlanOpts o;
+    o.slab = slab != 0;
+    if (const char *v = getenv("TGTK_SP_WAVES")) { o.waves = std::max(0.25, atof(v)); o.waves_set = true; }
+    if (const char *v = getenv("TGTK_SP_SPLIT")) o.split = std::min(0.9, std::max(0.1, atof(v)));
+    std::vector<int4> work;
+    plan_work_list(mask, X, nzt, nyt, x_lo, x_hi, slots, o, work);
+    *count = (int)(work.size() / 2);
+    if (items) {
+        if (cap < *count) return fail("tgtk_sparse_plan_host", "output too small");
+        for (int i = 0; i < *count; ++i) {
+            items[4 * i] = work[2 * i].x; items[4 * i + 1] = work[2 * i].y; items[4 * i + 2] = work[2 * i].z; items[4 * i + 3] = work[2 * i].w;
+        }
+    }
     return 0;
 }
 
