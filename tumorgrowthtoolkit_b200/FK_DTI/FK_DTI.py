@@ -89,7 +89,7 @@ class FK_DTI_Solver(FK_Solver):
 
         initial = _host.seed_gaussian(grid, init_scale)
         print("init: ", initial.shape, "Volume of init Tumor", np.sum(initial))   # FK_DTI.py:164
-        brainmask = np.max(rgb_lo, axis=-1) > 0
+        brainmask = _host.any_positive_last(rgb_lo)                                # FK_DTI.py:169: np.max(rgb, axis=-1) > 0
         box = _host.bounding_box(brainmask > 0.5, 2, brainmask.shape)             # FK_DTI.py:171
         record = _host.record_schedule(nsteps, n_series)
 

@@ -103,10 +103,34 @@ def record_schedule(nsteps, n_series):
 def bounding_box(mask, margin, shape):
     """Bounding box of the true voxels of `mask`, grown by `margin` and clamped
     (FK/FK.py:62-66).  Returns (min_coords, max_coords) as integer arrays."""
-    idx = np.argwhere(mask)
-    lo = np.maximum(idx.min(axis=0) - margin, 0)
-    hi = np.minimum(idx.max(axis=0) + margin + 1, shape)
+    mask = np.asarray(mask)
+    if mask.ndim != 3:                       # (the reference's argwhere form, any rank)
+        idx = np.argwhere(mask)
+        lo = np.maximum(idx.min(axis=0) - margin, 0)
+        hi = np.minimum(idx.max(axis=0) + margin + 1, shape)
+        return lo, hi
+    # same box from the three axis projections: argwhere materialises every true voxel's index triple (36 ms on the
+    # atlas), the projections are three passes over a byte array (4 ms)
+    mask = mask.astype(bool, copy=False)
+    zy = mask.any(axis=0)
+    proj = (mask.any(axis=(1, 2)), zy.any(axis=1), zy.any(axis=0))
+    if not proj[0].any():
+        raise ValueError("zero-size array to reduction operation minimum which has no identity")      # what argwhere().min() raises
+    first = np.array([int(np.argmax(q)) for q in proj])
+    last = np.array([len(q) - 1 - int(np.argmax(q[::-1])) for q in proj])
+    lo = np.maximum(first - margin, 0)
+    hi = np.minimum(last + margin + 1, shape)
     return lo, hi
+
+
+def any_positive_last(a):
+    """np.max(a, axis=-1) > 0 for an array whose last axis is short (the three rgb channels, FK_DTI.py:169): channel by
+    channel -- numpy's reduction over a strided axis of length 3 takes 0.3 s on the atlas, this 0.05 s.  NaN-free input."""
+    a = np.asarray(a)
+    out = a[..., 0] > 0
+    for c in range(1, a.shape[-1]):
+        out |= a[..., c] > 0
+    return out
 
 
 def crop(a, box):
