@@ -176,3 +176,31 @@ def test_dti_sparse_equals_dense(shape, precision):
     for p, q in zip(a["snapshots"], b["snapshots"]):
         assert np.array_equal(p, q)
     assert abs(a["volume"] - b["volume"]) <= 1e-12 * abs(b["volume"])
+
+
+@pytest.mark.parametrize("shape", [(9, 5, 7), (16, 3, 40), (8, 20, 33), (30, 9, 65)])
+def test_sparse_on_boxes_narrower_than_a_tile(shape):
+    """boxes smaller than one 8 x 32 tile in y or z (every halo wraps around inside the tile), forced sparse"""
+    from tumorgrowthtoolkit_b200 import _loop
+    rng = np.random.default_rng(7)
+    X, Y, Z = shape
+    wm = rng.uniform(0.2, 0.8, shape)
+    gm = 1.0 - wm
+    dead = np.zeros(shape, bool)
+    dead[: X // 3] = True                                   # a third of the planes outside the tissue ...
+    dead[:, :, Z // 2:] |= rng.uniform(size=(X, Y, Z - Z // 2)) < 0.3     # ... and scattered background elsewhere
+    wm[dead] = 0.0
+    gm[dead] = 0.0
+    u0 = np.zeros(shape)
+    u0[X // 2, Y // 2, Z // 4] = 0.8
+    u0[X // 2, Y // 2, (Z // 4 + 1) % Z] = 0.4
+    S0 = np.where(wm + gm >= 0.1, 1.0, 0.0)
+    out = {}
+    for sparse in (1, 0):
+        with _env(TGTK_SPARSE=sparse, TGTK_VARIANT=4):
+            out[sparse] = (_loop.fk2c_loop(*_args(wm, gm, u0, S0, 50)), _loop.fk_loop(u0, wm, gm, 0.1, 1.0, 10.0, 0.2, 0.03, 1.0, 1.0, 1.0, 50))
+    assert out[1][0]["sparse_items"] > 0 and out[1][1]["sparse_items"] > 0
+    for k in "PNS":
+        assert np.array_equal(out[1][0]["state"][k], out[0][0]["state"][k]), k
+    assert np.array_equal(out[1][1]["state"], out[0][1]["state"])
+    assert (out[1][1]["state"] > 0).sum() > 10

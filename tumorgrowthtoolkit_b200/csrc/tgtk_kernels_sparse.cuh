@@ -41,8 +41,12 @@ __global__ void __launch_bounds__(128) sparse_mask_kernel(const T *__restrict__ 
     const T closed = -Big<T>::v;
     if (z < Z) {
         for (int r = 0; r < 2; ++r) {
-            const int y = yt * 8 + 2 * w + r;
-            if (y >= Y) continue;
+            // Rows beyond the box (the last y tile of a box whose Y is not a multiple of 8) hold the periodically WRAPPED rows
+            // in the step kernels, and the first of them is the lower neighbour of the last row of the box: such a warp is
+            // live when the rows it mirrors are, or a box whose tissue touches its y faces would lose that coupling
+            // (tests/test_gpu_sparse.py::test_sparse_on_boxes_narrower_than_a_tile).  It stores nothing either way.
+            int y = yt * 8 + 2 * w + r;
+            if (y >= Y) y = (y - Y < Y) ? y - Y : (y - Y) % Y;
             const int64_t q = x * sx + y * sy + z;
             bool dead;
             if (mode == 0) {          // FK_2c: P, N; k, b
