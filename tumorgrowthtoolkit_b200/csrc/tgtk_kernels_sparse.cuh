@@ -42,11 +42,16 @@ __global__ void __launch_bounds__(128) sparse_mask_kernel(const T *__restrict__ 
     if (z < Z) {
         for (int r = 0; r < 2; ++r) {
             // Rows beyond the box (the last y tile of a box whose Y is not a multiple of 8) hold the periodically WRAPPED rows
-            // in the step kernels, and the first of them is the lower neighbour of the last row of the box: such a warp is
-            // live when the rows it mirrors are, or a box whose tissue touches its y faces would lose that coupling
-            // (tests/test_gpu_sparse.py::test_sparse_on_boxes_narrower_than_a_tile).  It stores nothing either way.
+            // in the step kernels, and the FIRST of them (y == Y, mirroring row 0) is the lower neighbour of the box's last
+            // row: where it starts a warp of its own (Y even) that warp is live when row 0 is, or a box whose tissue touches
+            // its y faces would lose the coupling (tests/test_gpu_sparse.py::test_sparse_on_boxes_narrower_than_a_tile).
+            // Such a warp stores nothing.  (Y odd: row Y is the second row of the warp that owns row Y-1 and is loaded with
+            // it.)  Later mirror rows are nobody's neighbour.
             int y = yt * 8 + 2 * w + r;
-            if (y >= Y) y = (y - Y < Y) ? y - Y : (y - Y) % Y;
+            if (y >= Y) {
+                if (y != Y) continue;
+                y = 0;
+            }
             const int64_t q = x * sx + y * sy + z;
             bool dead;
             if (mode == 0) {          // FK_2c: P, N; k, b
