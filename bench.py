@@ -787,7 +787,8 @@ def main():
                          "work_items": sparse["items"], "live_fraction": sparse["live_voxels"] / sparse["voxels"],
                          "moved_gbs": moved, "moved_frac": moved / peak},
                      "algorithmic_bytes_per_voxel_update": bpu, "kernel_us": 1e3 * launch_ms,
-                     "kernel": {"fk2c": "fk2c_step", "fk": "fk_step", "dti": "dti_step"}[pb["model"]] + "_v%d" % tuning["variant"],
+                     "kernel": {"fk2c": "fk2c_step", "fk": "fk_step", "dti": "dti_step"}[pb["model"]]
+                               + ("_sp (sparse launch of the two-voxel kernel)" if sparse["items"] > 0 else "_v%d" % tuning["variant"]),
                      "launch": tuning,
                      "shortcuts": None if dense is None else {
                          "what": "the dense launches with every voxel loaded, computed and stored (TGTK_SPARSE=0 TGTK_CLOSED_SKIP=0): no "
