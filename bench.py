@@ -658,7 +658,8 @@ def main():
                 "e2e": e2e, "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                              "peak_source": peak_src, "algorithmic_bytes_per_voxel_update": bpu, "kernel_us": kernel_us,
-                             "kernel": "dti_step_v4 (+ in-kernel halo push)" if args.slab_driver == "fused" else "dti_step",
+                             "kernel": "dti_step_sp (sparse launch over the rank's owned planes; dti_step_v4 where a slab has no dead space) + in-kernel halo push"
+                                       if args.slab_driver == "fused" else "dti_step",
                              "note": "per GPU: one rank's owned planes x algorithmic bytes / the step's share of the decomposed loop "
                                      "(exchange and synchronisation included)"},
                 "clocks": clocks, "wall_s_timed_region": wall, "slab": info, "slab_fk2c": info2, "ensemble": ens,
