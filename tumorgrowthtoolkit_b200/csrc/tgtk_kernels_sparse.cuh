@@ -326,8 +326,22 @@ __global__ void __launch_bounds__(128, MINB) fk2c_step_sp(const StepArgs<T> a, c
             SP_CLOCK(k2, fs_mid);
             const Pair<T> pu = tl[0][o0 - RS], pd = tl[0][o1 + RS];                       // rows y-1 and y+2: (P, k)
             const Pair<T> su = tl[1][o0 - RS], sd = tl[1][o1 + RS];                       // (S, b)
+#ifdef TGTK_SP_SHFL
+            // experiment: the z neighbours of lanes 1..30 by warp shuffle, shared memory only at the two ends of the warp
+            Pair<T> pl0 = {__shfl_up_sync(0xffffffffu, c0.p, 1), __shfl_up_sync(0xffffffffu, c0.k, 1)};
+            Pair<T> pr0 = {__shfl_down_sync(0xffffffffu, c0.p, 1), __shfl_down_sync(0xffffffffu, c0.k, 1)};
+            Pair<T> pl1 = {__shfl_up_sync(0xffffffffu, c1.p, 1), __shfl_up_sync(0xffffffffu, c1.k, 1)};
+            Pair<T> pr1 = {__shfl_down_sync(0xffffffffu, c1.p, 1), __shfl_down_sync(0xffffffffu, c1.k, 1)};
+            Pair<T> sl0 = {__shfl_up_sync(0xffffffffu, c0.s, 1), __shfl_up_sync(0xffffffffu, c0.b, 1)};
+            Pair<T> sr0 = {__shfl_down_sync(0xffffffffu, c0.s, 1), __shfl_down_sync(0xffffffffu, c0.b, 1)};
+            Pair<T> sl1 = {__shfl_up_sync(0xffffffffu, c1.s, 1), __shfl_up_sync(0xffffffffu, c1.b, 1)};
+            Pair<T> sr1 = {__shfl_down_sync(0xffffffffu, c1.s, 1), __shfl_down_sync(0xffffffffu, c1.b, 1)};
+            if (threadIdx.x == 0) { pl0 = tl[0][o0 - 1]; pl1 = tl[0][o1 - 1]; sl0 = tl[1][o0 - 1]; sl1 = tl[1][o1 - 1]; }
+            if (threadIdx.x == 31) { pr0 = tl[0][o0 + 1]; pr1 = tl[0][o1 + 1]; sr0 = tl[1][o0 + 1]; sr1 = tl[1][o1 + 1]; }
+#else
             const Pair<T> pl0 = tl[0][o0 - 1], pr0 = tl[0][o0 + 1], pl1 = tl[0][o1 - 1], pr1 = tl[0][o1 + 1];
             const Pair<T> sl0 = tl[1][o0 - 1], sr0 = tl[1][o0 + 1], sl1 = tl[1][o1 - 1], sr1 = tl[1][o1 + 1];
+#endif
             T sp0 = a.hy * (relu2(pu.b + c0.k) * (pu.a - c0.p) - fp_mid);
             T sp1 = a.hy * (fp_mid - relu2(c1.k + pd.b) * (c1.p - pd.a));
             T ss0 = a.gy * (relu2(su.b + c0.b) * (su.a - c0.s) - fs_mid);
