@@ -318,7 +318,16 @@ static bool exceeds_l2(const tgtk_sim *s)
 }
 static int effective_l2pf(const tgtk_sim *s)
 {
-    const int l2pf = (s->l2pf < 0) ? (exceeds_l2(s) ? 2 : 0) : s->l2pf;
+    // sparse launches only touch the live tiles: what has to fit in L2 is that share of the arrays (FK_DTI on the atlas box:
+    // 143 MB dense, 79 MB live -> no prefetch, 18.0 us per step against 18.4 with it)
+    bool beyond = exceeds_l2(s);
+    if (beyond && s->sp_active && s->n > 0) {
+        const tgtk_params &p = s->p;
+        const double touched = (double)(2 * s->nfields + s->ncoef) * (double)p.X * (double)s->sx * (double)s->elem;
+        const double owned = s->slab_on ? (double)s->slab_owned * p.Y * p.Z : (double)s->n;
+        beyond = touched * ((double)s->sp_live_voxels / owned) > 0.8 * (double)s->l2_bytes;
+    }
+    const int l2pf = (s->l2pf < 0) ? (beyond ? 2 : 0) : s->l2pf;
     return (l2pf > 0 && l2pf < s->p.X) ? l2pf : 0;
 }
 static bool effective_pdl(const tgtk_sim *s)
