@@ -112,3 +112,18 @@ def test_plan_all_dead_and_waves_override():
     one = nat.sparse_plan(mask, slots=592)
     assert len(many) > len(one)
     _check_cover(mask, many, 0, 145)
+
+
+def test_plan_rejects_bad_arguments():
+    mask = np.ones((8, 1, 1), dtype=np.uint32)
+    for kw in (dict(x_lo=5, x_hi=5), dict(x_lo=0, x_hi=9), dict(slots=0)):
+        with pytest.raises(nat.NativeError):
+            nat.sparse_plan(mask, **kw)
+
+
+def test_plan_items_are_ordered_longest_first():
+    mask = _brain_mask(145, 5, 23, seed=5)
+    items = nat.sparse_plan(mask, slots=592)
+    planes = items[:, 3] - items[:, 2]
+    # the list is sorted by modelled cost, which grows with the plane count: no late item is much longer than an early one
+    assert planes[: len(planes) // 4].mean() >= planes[-len(planes) // 4:].mean()
